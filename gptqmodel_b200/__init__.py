@@ -1,0 +1,10 @@
+"""gptqmodel_b200 — B200-native (sm_100a) GPTQ W4A16/W8A16 QuantLinear hot path.
+
+Public API:
+    B200QuantLinear   drop-in QuantLinear (reference contract: gptqmodel/nn_modules/qlinear)
+    lib / check       the raw C-ABI (include/b2q.h) through ctypes
+"""
+from ._lib import ABI_VERSION, B2QError, LIB_PATH, SYMBOLS, check, lib  # noqa: F401
+from .qlinear import B200QuantLinear  # noqa: F401
+
+__all__ = ["B200QuantLinear", "lib", "check", "B2QError", "LIB_PATH", "SYMBOLS", "ABI_VERSION"]

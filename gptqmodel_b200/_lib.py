@@ -1,0 +1,56 @@
+"""ctypes binding of libb2q.so (C-ABI declared in include/b2q.h).
+
+There is NO fallback: if the CUDA library is missing or fails to load, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2q.so")
+
+ABI_VERSION = 1
+
+# every symbol include/b2q.h declares: (restype, argtypes)
+_vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+SYMBOLS = {
+    "b2q_version": (_i, []),
+    "b2q_last_error": (ctypes.c_char_p, []),
+    "b2q_packed_bytes": (_sz, [_i, _i, _i]),
+    "b2q_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b2q_prepack": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b2q_mm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "b2q_gemv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b2q_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "b2q_permute_cols": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+}
+
+
+class B2QError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m gptqmodel_b200.build` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU/PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.b2q_version()
+    if v != ABI_VERSION:
+        raise ImportError(f"libb2q.so ABI version {v} != expected {ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise B2QError(f"{what} failed ({code}): {lib.b2q_last_error().decode(errors='replace')}")

@@ -1,0 +1,154 @@
+// b2q_api.cu — the extern "C" boundary declared in include/b2q.h: argument validation + tier dispatch.
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/b2q.h"
+#include "b2q_internal.h"
+
+namespace b2q {
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int check_cuda(int e, const char* what) {
+  if (e > 0) set_error("%s: CUDA error %d (%s)", what, e, cudaGetErrorString((cudaError_t)e));
+  return e;
+}
+
+static int validate(const char* fn, const void* x, const void* packed, const void* scales, const void* out, int M,
+                    int K, int N, int bits, int group_size, int dtype) {
+  if (x == nullptr || packed == nullptr || scales == nullptr || out == nullptr) {
+    set_error("%s: null pointer argument", fn);
+    return -2;
+  }
+  if (bits != 4 && bits != 8) {
+    set_error("%s: bits=%d not supported (4 or 8)", fn, bits);
+    return -2;
+  }
+  if (dtype != B2Q_DTYPE_F16 && dtype != B2Q_DTYPE_BF16) {
+    set_error("%s: dtype=%d not supported (0 fp16, 1 bf16)", fn, dtype);
+    return -2;
+  }
+  if (M < 0 || K <= 0 || N <= 0 || K % 32 != 0 || N % 32 != 0) {
+    set_error("%s: shape M=%d K=%d N=%d not supported (K, N multiples of 32)", fn, M, K, N);
+    return -2;
+  }
+  if (group_size < 32 || group_size % 32 != 0 || K % group_size != 0) {
+    set_error("%s: group_size=%d not supported for K=%d (multiple of 32 dividing K)", fn, group_size, K);
+    return -2;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(packed) & 15)) {
+    set_error("%s: x, out and packed must be 16-byte aligned", fn);
+    return -2;
+  }
+  return 0;
+}
+
+static MmArgs make_args(const void* x, const void* packed, const void* scales, const int32_t* qzeros,
+                        const int32_t* perm, const void* bias, void* out, int M, int K, int N, int bits,
+                        int group_size, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  MmArgs a;
+  a.x = x;
+  a.packed = packed;
+  a.scales = scales;
+  a.qzeros = qzeros;
+  a.perm = perm;
+  a.bias = bias;
+  a.out = out;
+  a.M = M;
+  a.K = K;
+  a.N = N;
+  a.bits = bits;
+  a.group_size = group_size;
+  a.dtype = dtype;
+  a.workspace = workspace;
+  a.workspace_bytes = workspace_bytes;
+  a.stream = (cudaStream_t)stream;
+  a.tune_ks = 0;
+  a.tune_warps = 0;
+  return a;
+}
+}  // namespace b2q
+
+using namespace b2q;
+
+extern "C" {
+
+int b2q_version(void) { return B2Q_ABI_VERSION; }
+
+const char* b2q_last_error(void) { return g_err; }
+
+size_t b2q_packed_bytes(int K, int N, int bits) { return (size_t)K * (size_t)N * (size_t)bits / 8; }
+
+size_t b2q_workspace_bytes(int M, int K, int N, int has_perm) {
+  (void)N;
+  return (has_perm && M > 1) ? (size_t)M * (size_t)K * 2 : 0;
+}
+
+int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K, int N, int bits, void* stream) {
+  if (qweight == nullptr || packed == nullptr) {
+    set_error("b2q_prepack: null pointer argument");
+    return -2;
+  }
+  if ((bits != 4 && bits != 8) || K <= 0 || N <= 0 || K % 32 != 0 || N % 32 != 0) {
+    set_error("b2q_prepack: bits=%d K=%d N=%d not supported (bits 4|8, K and N multiples of 32)", bits, K, N);
+    return -2;
+  }
+  return check_cuda(launch_prepack(qweight, perm, packed, K, N, bits, (cudaStream_t)stream), "b2q_prepack");
+}
+
+int b2q_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, void* stream) {
+  if (x == nullptr || perm == nullptr || out == nullptr || M < 0 || K <= 0) {
+    set_error("b2q_permute_cols: bad argument");
+    return -2;
+  }
+  if (M == 0) return 0;
+  return check_cuda(launch_permute_cols(x, perm, out, M, K, (cudaStream_t)stream), "b2q_permute_cols");
+}
+
+int b2q_gemv(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+             const void* bias, void* out, int K, int N, int bits, int group_size, int dtype, int ks, int warps,
+             void* stream) {
+  int v = validate("b2q_gemv", x, packed, scales, out, 1, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (ks > 16 || warps > 8 || (ks > 0 && (ks & (ks - 1)) != 0)) {
+    set_error("b2q_gemv: ks=%d (power of two <= 16) / warps=%d (<= 8) out of range", ks, warps);
+    return -2;
+  }
+  MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, 1, K, N, bits, group_size, dtype, nullptr, 0,
+                       stream);
+  a.tune_ks = ks;
+  a.tune_warps = warps;
+  return check_cuda(launch_gemv(a), "b2q_gemv");
+}
+
+int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+             const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
+             size_t workspace_bytes, void* stream) {
+  int v = validate("b2q_gemm", x, packed, scales, out, M, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (M == 0) return 0;
+  MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
+                       workspace_bytes, stream);
+  return check_cuda(launch_gemm(a), "b2q_gemm");
+}
+
+int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+           const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
+           size_t workspace_bytes, void* stream) {
+  int v = validate("b2q_mm", x, packed, scales, out, M, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (M == 0) return 0;
+  MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
+                       workspace_bytes, stream);
+  if (M == 1) return check_cuda(launch_gemv(a), "b2q_mm(gemv)");
+  return check_cuda(launch_gemm(a), "b2q_mm(gemm)");
+}
+
+}  // extern "C"

@@ -1,0 +1,433 @@
+// b2q_gemm.cu — prefill / batched path: out[M, N] = x[M, K] @ dequant(W)[K, N] (+ bias) on tcgen05 tensor cores.
+//
+// One CTA computes a (128*MT tokens) x (128 features) output tile, K in blocks of 64, with a STAGES-deep
+// mbarrier ring and warp-specialised roles:
+//   warp 0      producer : TMA (cp.async.bulk.tensor, SWIZZLE_128B) for the activation tile and cp.async.bulk
+//                          for the packed int4/int8 weight tile (contiguous 2 KB B2Q rows), one elected lane
+//   warp 1      MMA      : allocates TMEM, one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                          (M=128, N=128, K=16) with the fp32 accumulators in TMEM, tcgen05.commit -> mbarriers
+//   warps 2..5  dequant  : LDS.128 packed weights -> exact (q - z) * s in fp16/bf16 (integer subtract first, one
+//                          rounding: identical operands to the reference's torch dequant, qlinear/__init__.py:
+//                          1001-1003) -> 16-byte swizzled K-major st.shared -> fence.proxy.async -> mbarrier;
+//                          afterwards the same warps run the epilogue: tcgen05.ld TMEM -> regs -> (+bias) ->
+//                          fp16/bf16 -> 64-byte-per-thread coalesced global stores.
+// In the reference this is TorchLinear's dequant + torch.matmul (qlinear/torch.py:326-343), Marlin's
+// mma.sync kernel (marlin_template.h) and Swordfish's CUTLASS-derived prefill tier (swordfish_prefill_*.cuh).
+#include <cuda.h>
+
+#include "b2q_common.cuh"
+#include "b2q_internal.h"
+
+namespace b2q {
+
+constexpr int G_BN = 128;
+constexpr int G_BK = 64;
+constexpr int G_THREADS = 192;
+constexpr int G_DQ_THREADS = 128;
+
+template <int BITS, int MT, int STAGES>
+struct GemmCfg {
+  static constexpr int SUB = BITS / 4;
+  static constexpr int A_BYTES = MT * 128 * G_BK * 2;
+  static constexpr int B_BYTES = G_BN * G_BK * 2;
+  static constexpr int P_CHUNK_BYTES = 4 * SUB * 512;  // 4 feature tiles x 32 k
+  static constexpr int P_BYTES = 2 * P_CHUNK_BYTES;    // 2 k-chunks per 64-k block
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + P_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = MT * G_BN;
+};
+
+struct SZRaw {
+  uint32_t s;   // scale, 16-bit payload
+  uint32_t zw;  // packed zero word (or unused)
+};
+
+template <typename T, int BITS, bool ASYM>
+__device__ __forceinline__ SZRaw load_sz(const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, int g,
+                                         int n, int N) {
+  SZRaw r;
+  r.s = *reinterpret_cast<const uint16_t*>(scales + (size_t)g * N + n);
+  r.zw = 0;
+  if (ASYM) {
+    constexpr int PF = 32 / BITS;
+    r.zw = qzeros[(size_t)g * (N / PF) + n / PF];
+  }
+  return r;
+}
+
+// exact dequant of one packed uint4 (32 k of one feature for 4-bit, 16 k for 8-bit) into K-consecutive
+// 16-byte groups; out[i] holds 8 consecutive k.
+template <typename T, int BITS>
+struct Dequant;
+
+template <>
+struct Dequant<__half, 4> {
+  // z: integer zero point.  returns 4 x uint4 (32 halves)
+  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[4]) {
+    const uint32_t s2u = s16 | (s16 << 16);
+    const __half2 s2 = *reinterpret_cast<const __half2*>(&s2u);
+    const __half2 zlo = __float2half2_rn(1024.f + (float)z);   // exact
+    const __half2 zhi = __float2half2_rn(-(64.f + (float)z));  // exact
+    const __half2 sixteenth = __float2half2_rn(0.0625f);
+    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t h[4];
+      ET<__half>::unpack_w4(w[t], h);
+      __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[0]), zlo), s2);
+      __half2 v1 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[1]), sixteenth, zhi), s2);
+      __half2 v2 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[2]), zlo), s2);
+      __half2 v3 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[3]), sixteenth, zhi), s2);
+      o[t] = make_uint4(*reinterpret_cast<uint32_t*>(&v0), *reinterpret_cast<uint32_t*>(&v1),
+                        *reinterpret_cast<uint32_t*>(&v2), *reinterpret_cast<uint32_t*>(&v3));
+    }
+  }
+};
+
+template <>
+struct Dequant<__nv_bfloat16, 4> {
+  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[4]) {
+    const uint32_t s2u = s16 | (s16 << 16);
+    const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s2u);
+    const __nv_bfloat162 zb = __float2bfloat162_rn(128.f + (float)z);  // exact (<= 143)
+    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t h[4];
+      ET<__nv_bfloat16>::unpack_w4(w[t], h);
+      uint32_t r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 v = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[i]), zb), s2);
+        r[i] = *reinterpret_cast<uint32_t*>(&v);
+      }
+      o[t] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+  }
+};
+
+template <>
+struct Dequant<__half, 8> {
+  // 16 k per uint4 -> 2 x uint4
+  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[2]) {
+    const uint32_t s2u = s16 | (s16 << 16);
+    const __half2 s2 = *reinterpret_cast<const __half2*>(&s2u);
+    const __half2 zb = __float2half2_rn(1024.f + (float)z);  // exact (<= 1279)
+    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+    uint32_t r[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t p0 = __byte_perm(w[t], 0x64006400u, 0x7150);
+      uint32_t p1 = __byte_perm(w[t], 0x64006400u, 0x7352);
+      __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&p0), zb), s2);
+      __half2 v1 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&p1), zb), s2);
+      r[2 * t] = *reinterpret_cast<uint32_t*>(&v0);
+      r[2 * t + 1] = *reinterpret_cast<uint32_t*>(&v1);
+    }
+    o[0] = make_uint4(r[0], r[1], r[2], r[3]);
+    o[1] = make_uint4(r[4], r[5], r[6], r[7]);
+  }
+};
+
+template <>
+struct Dequant<__nv_bfloat16, 8> {
+  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[2]) {
+    const float s = __uint_as_float(s16 << 16);
+    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+    uint32_t r[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      // (q - z) exact in fp32, product with the bf16 scale exact in fp32, ONE rounding to bf16
+      const float q0 = (float)((int)(w[t] & 0xFFu) - z), q1 = (float)((int)((w[t] >> 8) & 0xFFu) - z);
+      const float q2 = (float)((int)((w[t] >> 16) & 0xFFu) - z), q3 = (float)((int)(w[t] >> 24) - z);
+      r[2 * t] = ET<__nv_bfloat16>::pack2(q0 * s, q1 * s);
+      r[2 * t + 1] = ET<__nv_bfloat16>::pack2(q2 * s, q3 * s);
+    }
+    o[0] = make_uint4(r[0], r[1], r[2], r[3]);
+    o[1] = make_uint4(r[4], r[5], r[6], r[7]);
+  }
+};
+
+template <typename T, int BITS, bool ASYM, int MT, int STAGES>
+__global__ void __launch_bounds__(G_THREADS, 1)
+    gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
+                const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, const T* __restrict__ bias,
+                T* __restrict__ out, int M, int K, int N, int group_size) {
+  using C = GemmCfg<BITS, MT, STAGES>;
+  using E = ET<T>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + STAGES * C::A_BYTES;
+  const uint32_t sP = sB + STAGES * C::B_BYTES;
+  const uint32_t sBar = sP + STAGES * C::P_BYTES;
+  const uint32_t bar_full = sBar, bar_bready = sBar + 8 * STAGES, bar_empty = sBar + 16 * STAGES;
+  const uint32_t bar_tfull = sBar + 24 * STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 24 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = N >> 5;
+  const int n0 = blockIdx.x * G_BN, m0 = blockIdx.y * (128 * MT);
+  const int nt0 = n0 >> 5;
+  const int ntiles = min(4, NT - nt0);
+  const int nkb = K / G_BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_bready + 8 * s, G_DQ_THREADS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      const uint32_t pbytes = (uint32_t)ntiles * C::SUB * 512u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, C::A_BYTES + 2 * pbytes);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+          tma_load_2d(sA + s * C::A_BYTES + mt * (128 * G_BK * 2), &tmap_x, bar_full + 8 * s, kb * G_BK,
+                      m0 + mt * 128);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          bulk_load(sP + s * C::P_BYTES + j * C::P_CHUNK_BYTES,
+                    packed + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = umma_idesc_f16(E::FMT, 128, G_BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(bar_full + 8 * s, ph);
+      mbar_wait(bar_bready + 8 * s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t bdesc = umma_desc_k_sw128(sB + s * C::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < G_BK / 16; ++k) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = umma_desc_k_sw128(sA + s * C::A_BYTES + mt * (128 * G_BK * 2));
+            umma_f16(tbase + mt * G_BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (kb == nkb - 1) umma_commit(bar_tfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ dequant warps ================================
+    const int t = threadIdx.x - 64;  // feature row inside the tile
+    const int n = n0 + t;
+    const bool nvalid = n < N;
+    const int nsafe = nvalid ? n : 0;
+    const int ntl = t >> 5;
+    constexpr int PF = 32 / BITS;
+    constexpr int ZSYM = 1 << (BITS - 1);
+    const int gchunks = group_size >> 5;  // 32-k chunks per group
+    // software-pipelined scale/zero fetch: [j] for the two 32-k chunks of a block
+    SZRaw cur[2], nxt[2];
+    cur[0] = load_sz<T, BITS, ASYM>(scales, qzeros, 0, nsafe, N);
+    cur[1] = load_sz<T, BITS, ASYM>(scales, qzeros, 1 / gchunks, nsafe, N);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      if (kb + 1 < nkb) {
+        nxt[0] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2) / gchunks, nsafe, N);
+        nxt[1] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 3) / gchunks, nsafe, N);
+      }
+      mbar_wait(bar_full + 8 * s, ph);
+      const uint32_t brow = sB + s * C::B_BYTES + t * 128;
+      const uint32_t sw = (uint32_t)(t & 7);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        int z = ZSYM;
+        if (ASYM) z = (int)((cur[j].zw >> (BITS * (nsafe % PF))) & ((1u << BITS) - 1));
+        const uint4* pj = reinterpret_cast<const uint4*>(smem + (sP - smem_base) + s * C::P_BYTES +
+                                                         j * C::P_CHUNK_BYTES);
+        if (BITS == 4) {
+          const uint4 pv = pj[ntl * 32 + lane];
+          uint4 o[4];
+          Dequant<T, 4>::run(pv, cur[j].s, z, o);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = brow + (((uint32_t)(j * 4 + c) ^ sw) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[c].x), "r"(o[c].y),
+                         "r"(o[c].z), "r"(o[c].w)
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 pv = pj[(ntl * 2 + h) * 32 + lane];
+            uint4 o[2];
+            Dequant<T, 8>::run(pv, cur[j].s, z, o);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const uint32_t addr = brow + (((uint32_t)(j * 4 + h * 2 + c) ^ sw) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[c].x), "r"(o[c].y),
+                           "r"(o[c].z), "r"(o[c].w)
+                           : "memory");
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_bready + 8 * s);
+      cur[0] = nxt[0];
+      cur[1] = nxt[1];
+    }
+
+    // ================================ epilogue ================================
+    mbar_wait(bar_tfull, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = m0 + mt * 128 + q * 32 + lane;
+#pragma unroll
+      for (int cc = 0; cc < G_BN / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tbase + ((uint32_t)(q * 32) << 16) + mt * G_BN + cc * 32, r);
+        tmem_ld_wait();
+        const int nc = n0 + cc * 32;
+        if (row < M && nc < N) {
+          T* dst = out + (size_t)row * N + nc;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              // reference order: round the matmul to the output dtype, then add bias (torch.py:337-342)
+              float f0 = __uint_as_float(r[v * 8 + 2 * i]), f1 = __uint_as_float(r[v * 8 + 2 * i + 1]);
+              if (bias != nullptr) {
+                f0 = E::to_f(E::from_f(f0)) + E::to_f(bias[nc + v * 8 + 2 * i]);
+                f1 = E::to_f(E::from_f(f1)) + E::to_f(bias[nc + v * 8 + 2 * i + 1]);
+              }
+              pk[i] = E::pack2(f0, f1);
+            }
+            *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tbase, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_x_tmap(CUtensorMap* map, const void* x, int M, int K, int dtype) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("b2q_gemm: cuTensorMapEncodeTiled not available from the driver");
+    return -1;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)G_BK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("b2q_gemm: cuTensorMapEncodeTiled failed (%d) for x=%p M=%d K=%d", (int)r, x, M, K);
+    return -1;
+  }
+  return 0;
+}
+
+template <typename T, int BITS, bool ASYM, int MT, int STAGES>
+static int launch_gemm_t(const MmArgs& a, const void* x) {
+  using C = GemmCfg<BITS, MT, STAGES>;
+  CUtensorMap tmap;
+  if (make_x_tmap(&tmap, x, a.M, a.K, a.dtype) != 0) return -1;
+  auto kern = gemm_kernel<T, BITS, ASYM, MT, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("b2q_gemm: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  dim3 grid((a.N + G_BN - 1) / G_BN, (a.M + 128 * MT - 1) / (128 * MT), 1);
+  kern<<<grid, G_THREADS, C::SMEM_BYTES, a.stream>>>(tmap, (const uint4*)a.packed, (const T*)a.scales,
+                                                     (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M,
+                                                     a.K, a.N, a.group_size);
+  return (int)cudaGetLastError();
+}
+
+int launch_gemm(const MmArgs& a) {
+  if (a.K % G_BK != 0) {
+    set_error("b2q_gemm: K=%d must be a multiple of %d", a.K, G_BK);
+    return -1;
+  }
+  const void* x = a.x;
+  if (a.perm != nullptr) {
+    const size_t need = (size_t)a.M * a.K * 2;
+    if (a.workspace == nullptr || a.workspace_bytes < need) {
+      set_error("b2q_gemm: act-order needs a %zu-byte workspace (got %zu)", need, a.workspace_bytes);
+      return -1;
+    }
+    int e = launch_permute_cols(a.x, a.perm, a.workspace, a.M, a.K, a.stream);
+    if (e != 0) return e;
+    x = a.workspace;
+  }
+  const bool asym = a.qzeros != nullptr;
+  const bool big = a.M > 128;
+#define B2Q_GEMM_CASE(T, BITS, ST)                                                              \
+  (asym ? (big ? launch_gemm_t<T, BITS, true, 2, ST>(a, x) : launch_gemm_t<T, BITS, true, 1, ST>(a, x)) \
+        : (big ? launch_gemm_t<T, BITS, false, 2, ST>(a, x) : launch_gemm_t<T, BITS, false, 1, ST>(a, x)))
+  if (a.dtype == 0) return a.bits == 4 ? B2Q_GEMM_CASE(__half, 4, 4) : B2Q_GEMM_CASE(__half, 8, 3);
+  return a.bits == 4 ? B2Q_GEMM_CASE(__nv_bfloat16, 4, 4) : B2Q_GEMM_CASE(__nv_bfloat16, 8, 3);
+#undef B2Q_GEMM_CASE
+}
+
+}  // namespace b2q

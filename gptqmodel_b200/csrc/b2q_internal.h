@@ -1,0 +1,33 @@
+// b2q_internal.h — launchers shared between the .cu translation units (not part of the public C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2q {
+
+struct MmArgs {
+  const void* x;        // [M, K] fp16/bf16, contiguous
+  const void* packed;   // B2Q tiles
+  const void* scales;   // [G, N] same dtype as x
+  const void* qzeros;   // int32 [G, N*bits/32] (v2: true zero-points) or nullptr when symmetric
+  const int32_t* perm;  // [K] act-order row permutation (k' -> original k) or nullptr
+  const void* bias;     // [N] or nullptr
+  void* out;            // [M, N]
+  int M, K, N;
+  int bits;        // 4 | 8
+  int group_size;  // 32 | 64 | 128 | K
+  int dtype;       // 0 fp16, 1 bf16
+  void* workspace;
+  size_t workspace_bytes;
+  cudaStream_t stream;
+  int tune_ks;     // >0: force GEMV cluster size (split-K)
+  int tune_warps;  // >0: force GEMV warps per CTA
+};
+
+int launch_prepack(const void* qweight, const int32_t* perm, void* out, int K, int N, int bits, cudaStream_t stream);
+int launch_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, cudaStream_t stream);
+int launch_gemv(const MmArgs& a);
+int launch_gemm(const MmArgs& a);
+void set_error(const char* fmt, ...);
+
+}  // namespace b2q

@@ -1,0 +1,84 @@
+// b2q_prepack.cu — one-time repack of the GPTQ checkpoint layout into B2Q tiles (see b2q_common.cuh).
+//
+// Source layout (reference: gptqmodel/nn_modules/qlinear/__init__.py:827-865, packer :1536-1539):
+//   qweight int32 [K*bits/32, N] row-major; word [i, n] holds rows i*pf..i*pf+pf-1 of column n, row i*pf+j at
+//   bits [bits*j, bits*(j+1)).
+// The role of this kernel is the one gptq_marlin_repack / swordfish_prepack_B play in the reference's
+// post_init (qlinear/marlin.py:246-293, qlinear/swordfish.py:221-297): load-time only, not on the hot path.
+#include "b2q_common.cuh"
+#include "b2q_internal.h"
+
+namespace b2q {
+
+template <int BITS>
+__global__ void prepack_kernel(const uint32_t* __restrict__ qweight, const int32_t* __restrict__ perm,
+                               uint4* __restrict__ out, int K, int N) {
+  constexpr int SUB = BITS / 4;  // uint4 per (chunk, feature): 1 for 4-bit, 2 for 8-bit
+  const int NT = N / 32;
+  const long long total = (long long)(K / 32) * NT * SUB * 32;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int lane = (int)(idx & 31);
+  long long rest = idx >> 5;
+  const int h = (int)(rest % SUB);
+  rest /= SUB;
+  const int nt = (int)(rest % NT);
+  const int kc = (int)(rest / NT);
+  const int n = nt * 32 + lane;
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t word = 0;
+    if (BITS == 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // nibble position i holds k-offset {0,2,4,6,1,3,5,7}[i]
+        const int koff = (i < 4) ? (2 * i) : (2 * (i - 4) + 1);
+        const int kp = kc * 32 + j * 8 + koff;
+        const int k = perm ? perm[kp] : kp;
+        const uint32_t q = (qweight[(size_t)(k >> 3) * N + n] >> (4 * (k & 7))) & 0xFu;
+        word |= q << (4 * i);
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int kp = kc * 32 + h * 16 + j * 4 + b;
+        const int k = perm ? perm[kp] : kp;
+        const uint32_t q = (qweight[(size_t)(k >> 2) * N + n] >> (8 * (k & 3))) & 0xFFu;
+        word |= q << (8 * b);
+      }
+    }
+    w[j] = word;
+  }
+  out[idx] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int launch_prepack(const void* qweight, const int32_t* perm, void* out, int K, int N, int bits,
+                   cudaStream_t stream) {
+  const long long total = (long long)(K / 32) * (N / 32) * (bits / 4) * 32;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  if (bits == 4)
+    prepack_kernel<4><<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)qweight, perm, (uint4*)out, K, N);
+  else
+    prepack_kernel<8><<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)qweight, perm, (uint4*)out, K, N);
+  return (int)cudaGetLastError();
+}
+
+// x'[m, k'] = x[m, perm[k']]  (act-order activation gather for the GEMM path; the GEMV fuses it).
+// Same job as permute_cols_kernel in the reference's Marlin (gptq_marlin.cu:86-164).
+template <typename T>
+__global__ void permute_cols_kernel(const T* __restrict__ x, const int32_t* __restrict__ perm, T* __restrict__ out,
+                                    int M, int K) {
+  for (int m = blockIdx.y; m < M; m += gridDim.y)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x)
+      out[(size_t)m * K + k] = x[(size_t)m * K + perm[k]];
+}
+
+int launch_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, cudaStream_t stream) {
+  dim3 grid((K + 255) / 256 > 64 ? 64 : (K + 255) / 256, M > 32768 ? 32768 : M);
+  permute_cols_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)x, perm, (uint16_t*)out, M, K);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b2q

@@ -1,0 +1,290 @@
+"""B200QuantLinear — drop-in GPTQ QuantLinear whose forward() runs hand-written sm_100a CUDA.
+
+Mirrors the class contract of the reference's kernels:
+  constructor / buffers : gptqmodel/nn_modules/qlinear/__init__.py:664-692, 827-865 (qweight, qzeros, scales, g_idx,
+                          bias in CHECKPOINT layout so a loader can fill them), qlinear/swordfish.py:66-148
+  capability attributes : qlinear/swordfish.py:40-62 / qlinear/marlin.py:59-75 (`SUPPORTS_*`, REQUIRES_FORMAT_V2)
+  validate()/validate_once() -> (ok, err), NotImplementedError = "try the next kernel" (utils/model.py:703-707)
+  post_init()           : one-time repack after the weights are on the device (qlinear/marlin.py:246-293)
+  forward(x)            : x [..., K] fp16/bf16 -> [..., N] same dtype, bias added, adapter applied
+                          (qlinear/swordfish.py:305-355, qlinear/torch.py:302-347)
+
+The module is stand-alone (no import of the reference package); INTEGRATION.md shows the 20-line file a
+maintainer drops into gptqmodel/nn_modules/qlinear/ to register it with the reference's kernel selection.
+There is no CPU / PyTorch fallback: every forward goes through libb2q.so (include/b2q.h) or raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from ._lib import B2QError, check, lib
+
+_DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class B200QuantLinear(nn.Module):
+    # ---- capability declaration (names follow the reference's BaseQuantLinear) ----
+    SUPPORTS_BACKENDS = ["b200"]
+    SUPPORTS_METHODS = ["gptq"]
+    SUPPORTS_FORMATS = {"gptq": 110, "gptq_v2": 110}  # > Swordfish (101) / Machete (100) / Marlin (90)
+    SUPPORTS_BITS = [4, 8]
+    SUPPORTS_GROUP_SIZE = [-1, 32, 64, 128]
+    SUPPORTS_DESC_ACT = [True, False]
+    SUPPORTS_SYM = [True, False]
+    SUPPORTS_SHARDS = True
+    SUPPORTS_TRAINING = False
+    SUPPORTS_AUTO_PADDING = False
+    SUPPORTS_IN_FEATURES_DIVISIBLE_BY = [64]
+    SUPPORTS_OUT_FEATURES_DIVISIBLE_BY = [32]
+    SUPPORTS_PACK_DTYPES = [torch.int32]
+    SUPPORTS_ADAPTERS = []  # any object with .apply(x=, out=) works; see forward()
+    SUPPORTS_DEVICES = ["cuda"]
+    SUPPORTS_PLATFORM = ["linux"]
+    SUPPORTS_DTYPES = [torch.float16, torch.bfloat16]
+    REQUIRES_FORMAT_V2 = True  # qzeros hold the true zero-point (loader adds 0x11111111 to v1 files)
+    QUANT_TYPE = "b200"
+
+    def __init__(
+        self,
+        bits: int,
+        group_size: int,
+        desc_act: bool,
+        sym: bool,
+        in_features: int,
+        out_features: int,
+        bias: bool = False,
+        pack_dtype: torch.dtype = torch.int32,
+        adapter=None,
+        register_buffers: bool = True,
+        **kwargs,
+    ):
+        super().__init__()
+        ok, err = self.validate(
+            bits=bits, group_size=group_size, desc_act=desc_act, sym=sym, in_features=in_features,
+            out_features=out_features, pack_dtype=pack_dtype, dtype=kwargs.get("dtype"),
+        )
+        if not ok:
+            raise err
+        self.bits = bits
+        self.requested_group_size = group_size
+        self.group_size = group_size if group_size != -1 else in_features
+        self.desc_act = desc_act
+        self.sym = sym
+        self.in_features = in_features
+        self.out_features = out_features
+        self.pack_dtype = pack_dtype
+        self.pack_dtype_bits = 32
+        self.pack_factor = 32 // bits
+        self.maxq = (1 << bits) - 1
+        self.name = kwargs.get("name") or f"{self.__class__.__module__}.{self.__class__.__qualname__}"
+        self.backend = kwargs.get("backend", "b200")
+        self.compute_dtype = kwargs.get("dtype") or torch.float16
+        self.adapter = adapter
+        self._qzeros_format = 2
+        self._prepacked = False
+        self._scales_cache = {}
+
+        K, N, G = in_features, out_features, math.ceil(in_features / self.group_size)
+        # checkpoint-shaped, non-trainable Parameters (what Marlin/Swordfish register: swordfish.py:108-148)
+        mk = lambda t: nn.Parameter(t, requires_grad=False)  # noqa: E731
+        if register_buffers:
+            self.qweight = mk(torch.zeros((K * bits // 32, N), dtype=torch.int32))
+            self.qzeros = mk(torch.zeros((G, N * bits // 32), dtype=torch.int32))
+            self.scales = mk(torch.zeros((G, N), dtype=torch.float16))
+            self.g_idx = mk(torch.tensor([i // self.group_size for i in range(K)], dtype=torch.int32))
+            self.bias = mk(torch.zeros(N, dtype=torch.float16)) if bias else None
+        else:
+            self.qweight = self.qzeros = self.scales = self.g_idx = None
+            self.bias = None
+        # runtime tensors created by post_init()
+        self.packed: Optional[torch.Tensor] = None
+        self.perm: Optional[torch.Tensor] = None
+        self._zeros_dev: Optional[torch.Tensor] = None
+
+    # ---- validation -------------------------------------------------------------------------------
+    @classmethod
+    def validate_once(cls) -> Tuple[bool, Optional[Exception]]:
+        if not torch.cuda.is_available():
+            return False, NotImplementedError("B200QuantLinear needs a CUDA device")
+        major, minor = torch.cuda.get_device_capability()
+        if major != 10:
+            return False, NotImplementedError(f"B200QuantLinear is built for sm_100a only, found sm_{major}{minor}")
+        return True, None
+
+    @classmethod
+    def validate(cls, bits: int, group_size: int = -1, desc_act: bool = False, sym: bool = True,
+                 in_features: int = None, out_features: int = None, pack_dtype: torch.dtype = None,
+                 dtype: Optional[torch.dtype] = None, **_ignored) -> Tuple[bool, Optional[Exception]]:
+        """Static parameter check; NotImplementedError means "unsupported here, try the next kernel"."""
+        if bits not in cls.SUPPORTS_BITS:
+            return False, NotImplementedError(f"{cls.__name__}: bits={bits} not in {cls.SUPPORTS_BITS}")
+        if group_size not in cls.SUPPORTS_GROUP_SIZE:
+            return False, NotImplementedError(f"{cls.__name__}: group_size={group_size} not in {cls.SUPPORTS_GROUP_SIZE}")
+        if pack_dtype is not None and pack_dtype not in cls.SUPPORTS_PACK_DTYPES:
+            return False, NotImplementedError(f"{cls.__name__}: pack_dtype={pack_dtype} unsupported")
+        if dtype is not None and dtype not in cls.SUPPORTS_DTYPES:
+            return False, NotImplementedError(f"{cls.__name__}: dtype={dtype} unsupported")
+        if in_features is not None:
+            if in_features % 64 != 0:
+                return False, NotImplementedError(f"{cls.__name__}: in_features={in_features} must be divisible by 64")
+            if group_size != -1 and in_features % group_size != 0:
+                return False, NotImplementedError(f"{cls.__name__}: in_features % group_size != 0")
+        if out_features is not None and out_features % 32 != 0:
+            return False, NotImplementedError(f"{cls.__name__}: out_features={out_features} must be divisible by 32")
+        return True, None
+
+    def qzero_format(self, format: int = None) -> int:
+        if format is None:
+            return self._qzeros_format
+        if format not in (1, 2):
+            raise ValueError("Unsupported qzero format. Only 1 and 2 are supported.")
+        self._qzeros_format = format
+        return format
+
+    def convert_gptq_v1_to_v2(self):
+        """In-place v1 -> v2 zero-points (what utils/model.py:810-818 does when REQUIRES_FORMAT_V2)."""
+        if self._qzeros_format == 1:
+            off = {4: 0x11111111, 8: 0x01010101}[self.bits]
+            self.qzeros.data += off
+            self._qzeros_format = 2
+
+    def list_buffers(self):
+        out, seen = [], set()
+        for state in (self._parameters, self._buffers):
+            for t in state.values():
+                if isinstance(t, torch.Tensor) and id(t) not in seen:
+                    seen.add(id(t))
+                    out.append(t)
+        for t in (self.packed, self.perm, self._zeros_dev):
+            if isinstance(t, torch.Tensor) and id(t) not in seen:
+                out.append(t)
+        return out
+
+    # ---- one-time repack ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def post_init(self):
+        if self._prepacked:
+            return
+        dev = self.qweight.device
+        if dev.type != "cuda":
+            raise B2QError("B200QuantLinear.post_init(): weights must be on a CUDA device (no CPU path)")
+        if self._qzeros_format != 2:
+            raise B2QError("B200QuantLinear needs v2 qzeros; call convert_gptq_v1_to_v2() after loading a v1 file")
+        K, N = self.in_features, self.out_features
+        gs = self.group_size
+        with torch.cuda.device(dev):
+            # act-order: sort rows by group so every group is contiguous; x is gathered with the same permutation
+            g_idx = self.g_idx.data.to(torch.int64)
+            trivial = torch.equal(g_idx, torch.arange(K, device=dev) // gs)
+            perm = None
+            if not trivial:
+                counts = torch.bincount(g_idx, minlength=K // gs)
+                if counts.numel() != K // gs or not bool((counts == gs).all()):
+                    raise NotImplementedError(
+                        "B200QuantLinear: g_idx must assign exactly group_size rows to every group")
+                perm = torch.argsort(g_idx, stable=True).to(torch.int32).contiguous()
+            # symmetric layers (every zero-point == 2^(bits-1)) never read qzeros
+            zsym = {4: 0x88888888 - (1 << 32), 8: 0x80808080 - (1 << 32)}[self.bits]
+            is_sym = bool((self.qzeros.data == zsym).all())
+            packed = torch.empty(lib.b2q_packed_bytes(K, N, self.bits), dtype=torch.uint8, device=dev)
+            qw = self.qweight.data.contiguous()
+            check(lib.b2q_prepack(_ptr(qw), _ptr(perm), _ptr(packed), K, N, self.bits,
+                                  torch.cuda.current_stream(dev).cuda_stream), "b2q_prepack")
+            torch.cuda.current_stream(dev).synchronize()
+        self.packed = packed
+        self.perm = perm
+        self._zeros_dev = None if is_sym else self.qzeros.data.contiguous()
+        self._is_sym = is_sym
+        # the checkpoint-layout weights are no longer needed (Marlin/Swordfish free them as well)
+        self.qweight = nn.Parameter(torch.empty(0, dtype=torch.int32, device=dev), requires_grad=False)
+        self.g_idx = nn.Parameter(torch.empty(0, dtype=torch.int32, device=dev), requires_grad=False)
+        self.scales.data = self.scales.data.contiguous()
+        self._prepacked = True
+        if self.adapter is not None and hasattr(self.adapter, "post_init"):
+            self.adapter.post_init(weight_key=self.name, device=dev,
+                                   lora_A=getattr(self, "lora_A", None), lora_B=getattr(self, "lora_B", None))
+
+    def _scales_for(self, dtype: torch.dtype) -> torch.Tensor:
+        s = self.scales.data
+        if s.dtype == dtype:
+            return s
+        c = self._scales_cache.get(dtype)
+        if c is None or c.device != s.device:
+            c = s.to(dtype).contiguous()  # Marlin re-casts scales to x.dtype the same way (marlin.py:312-315)
+            self._scales_cache[dtype] = c
+        return c
+
+    def _bias_for(self, dtype: torch.dtype) -> Optional[torch.Tensor]:
+        if self.bias is None:
+            return None
+        b = self.bias.data
+        if b.dtype == dtype:
+            return b
+        key = ("bias", dtype)
+        c = self._scales_cache.get(key)
+        if c is None or c.device != b.device:
+            c = b.to(dtype).contiguous()
+            self._scales_cache[key] = c
+        return c
+
+    # ---- hot path ------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self._prepacked:
+            raise B2QError("B200QuantLinear.forward() before post_init()")
+        K, N = self.in_features, self.out_features
+        out_shape = x.shape[:-1] + (N,)
+        if x.shape[-1] != K:
+            raise ValueError(f"expected last dim {K}, got {x.shape[-1]}")
+        if x.dtype not in _DTYPE_CODE:
+            raise B2QError(f"B200QuantLinear supports fp16/bf16 activations, got {x.dtype}")
+        if x.device != self.packed.device:
+            raise B2QError(f"input on {x.device} but weights on {self.packed.device}")
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+        if M == 0:
+            return out.reshape(out_shape)
+        ws, ws_bytes = None, 0
+        if self.perm is not None and M > 1:
+            ws_bytes = lib.b2q_workspace_bytes(M, K, N, 1)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        check(
+            lib.b2q_mm(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)), _ptr(self._zeros_dev),
+                       _ptr(self.perm), _ptr(self._bias_for(x.dtype)), _ptr(out), M, K, N, self.bits,
+                       self.group_size, _DTYPE_CODE[x.dtype], _ptr(ws), ws_bytes,
+                       torch.cuda.current_stream(x.device).cuda_stream),
+            "b2q_mm",
+        )
+        out = out.reshape(out_shape)
+        if self.adapter:
+            out = self.adapter.apply(x=x, out=out)
+        return out
+
+    # ---- helpers for tests / tools -------------------------------------------------------------------
+    @classmethod
+    def from_checkpoint_tensors(cls, qweight, qzeros, scales, g_idx, bits, group_size, bias=None, desc_act=None,
+                                sym=None, device="cuda", dtype=None):
+        """Build + post_init a module from checkpoint-layout tensors (v2 qzeros)."""
+        K = g_idx.shape[0]
+        N = qweight.shape[1]
+        m = cls(bits=bits, group_size=group_size, desc_act=bool(desc_act), sym=bool(sym) if sym is not None else True,
+                in_features=K, out_features=N, bias=bias is not None, register_buffers=False, dtype=dtype)
+        mk = lambda t: nn.Parameter(t.detach().clone().contiguous().to(device), requires_grad=False)  # noqa: E731
+        m.qweight, m.qzeros, m.scales, m.g_idx = mk(qweight), mk(qzeros), mk(scales), mk(g_idx.to(torch.int32))
+        m.bias = mk(bias) if bias is not None else None
+        m.post_init()
+        return m
+
+    def extra_repr(self) -> str:
+        return (f"in_features={self.in_features}, out_features={self.out_features}, bits={self.bits}, "
+                f"group_size={self.group_size}, desc_act={self.desc_act}, sym={self.sym}")

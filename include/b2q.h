@@ -1,0 +1,77 @@
+/* b2q.h — C ABI of libb2q.so: the B200-native (sm_100a) GPTQ W4A16/W8A16 QuantLinear hot path.
+ *
+ * This is the boundary a host framework binds (ctypes / cffi / a torch.library shim); no torch or C++ types cross
+ * it.  All pointers are DEVICE pointers unless noted, all calls are asynchronous on `stream` (a cudaStream_t passed
+ * as void*), no call allocates, synchronises or throws; every call returns 0 on success or a non-zero code and
+ * leaves a message for b2q_last_error().
+ *
+ * Reference interfaces replaced (paths relative to ModelCloud/GPTQModel):
+ *   b2q_prepack  <- the post_init repack ops: gptq_marlin_repack (gptqmodel/nn_modules/qlinear/marlin.py:246-293,
+ *                   gptqmodel_ext/marlin/gptq_marlin_repack.cu:254) and swordfish_prepack_B
+ *                   (gptqmodel/nn_modules/qlinear/swordfish.py:221-297, gptqmodel/utils/swordfish.py:292-311)
+ *   b2q_mm       <- the forward ops: torch.ops.gptqmodel_swordfish.swordfish_mm (gptqmodel_ext/swordfish/.../
+ *                   swordfish_mm.cu:290-444), gptq_marlin_gemm (gptqmodel/utils/marlin.py:562-608), and the torch
+ *                   oracle TorchLinear._forward_eager (gptqmodel/nn_modules/qlinear/torch.py:326-347)
+ *   b2q_permute_cols <- Marlin's permute_cols_kernel (gptqmodel_ext/marlin/gptq_marlin.cu:86-164) / the
+ *                   x[:, perm] gather in SwordfishLinear.forward (qlinear/swordfish.py:314-318)
+ *
+ * Checkpoint tensors consumed (gptqmodel/nn_modules/qlinear/__init__.py:827-865):
+ *   qweight int32 [K*bits/32, N], qzeros int32 [G, N*bits/32] (v2 = true zero-point), scales [G, N],
+ *   g_idx int32 [K].  The host derives perm = stable argsort(g_idx) for act-order layers.
+ */
+#ifndef B2Q_H_
+#define B2Q_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2Q_ABI_VERSION 1
+#define B2Q_DTYPE_F16 0
+#define B2Q_DTYPE_BF16 1
+
+/* ABI version of the loaded library (B2Q_ABI_VERSION). */
+int b2q_version(void);
+
+/* Message of the last failing call on this thread ("" if none). Host pointer, valid until the next failure. */
+const char* b2q_last_error(void);
+
+/* Size in bytes of the prepacked weight buffer (== K*N*bits/8: the repack is a permutation). */
+size_t b2q_packed_bytes(int K, int N, int bits);
+
+/* Workspace b2q_mm needs for M rows (0 unless the layer has an act-order permutation and M > 1). */
+size_t b2q_workspace_bytes(int M, int K, int N, int has_perm);
+
+/* Repack checkpoint-layout qweight into B2Q tiles.  perm (int32 [K], k' -> original row) may be NULL.
+ * Requires K % 32 == 0, N % 32 == 0, bits in {4, 8}. */
+int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K, int N, int bits, void* stream);
+
+/* out[M, N] = x[M, K] @ dequant(W) (+ bias).  Dispatches on M inside the library (M == 1: cluster split-K GEMV,
+ * otherwise the tcgen05 GEMM) so a CUDA graph sees the true M.
+ *   x, scales, bias, out : fp16 (dtype 0) or bf16 (dtype 1), all the same type; x and out contiguous row-major
+ *   qzeros               : NULL for symmetric layers (zero-point 2^(bits-1)), else int32 [G, N*bits/32]
+ *   perm                 : NULL, or int32 [K] act-order permutation used at prepack
+ *   group_size           : 32 | 64 | 128 | K (per-channel; the reference's -1)
+ *   workspace            : >= b2q_workspace_bytes(M, K, N, perm != NULL) bytes, may be NULL when that is 0 */
+int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+           const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
+           size_t workspace_bytes, void* stream);
+
+/* The two tiers individually (tests, benchmarks, tuning).  b2q_gemv requires M == 1; ks/warps <= 0 = heuristic. */
+int b2q_gemv(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+             const void* bias, void* out, int K, int N, int bits, int group_size, int dtype, int ks, int warps,
+             void* stream);
+int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+             const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
+             size_t workspace_bytes, void* stream);
+
+/* out[m, k'] = x[m, perm[k']] for 16-bit elements. */
+int b2q_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2Q_H_ */

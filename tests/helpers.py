@@ -1,0 +1,79 @@
+"""Shared fixtures: synthetic quantised layers built with the oracle's packer (restated pack_original)."""
+import torch
+
+import oracle
+
+
+def make_layer(K, N, bits=4, group_size=128, sym=True, desc_act=False, bias=False, seed=42, dtype=torch.float16):
+    """Returns dict of CPU checkpoint-layout tensors (v2 qzeros) quantised from randn weights.
+
+    Recipe follows SURVEY.md §8(d): W = randn(N, K, seed) * 0.5, sym grid of tests/kernels/test_swordfish.py:31-56
+    or min/max asym, act-order g_idx = (arange // g)[randperm].
+    """
+    gen = torch.Generator().manual_seed(seed)
+    W = torch.randn(N, K, generator=gen) * 0.5
+    gs = group_size if group_size > 0 else K
+    if desc_act:
+        _, g_idx = oracle.make_act_order(K, gs, seed=seed)
+    else:
+        g_idx = torch.arange(K, dtype=torch.int32) // gs
+    # vectorised min/max quantiser (same grid as oracle.quantize_sym / quantize_asym)
+    G = K // gs
+    order = torch.argsort(g_idx.long(), stable=True)
+    Wg = W[:, order].reshape(N, G, gs)
+    maxq = (1 << bits) - 1
+    if sym:
+        m = Wg.abs().amax(dim=2).clamp(min=1e-5)
+        scales = m / ((maxq + 1) // 2 - 1)
+        zeros = torch.full((N, G), float((maxq + 1) // 2))
+    else:
+        lo = Wg.amin(dim=2).clamp(max=0)
+        hi = Wg.amax(dim=2).clamp(min=0)
+        scales = ((hi - lo) / maxq).clamp(min=1e-5)
+        zeros = torch.round(-lo / scales).clamp(0, maxq)
+    qw, qz, sc, gi = oracle.pack(W, scales, zeros, g_idx, bits)
+    b = None
+    if bias:
+        b = (torch.randn(N, generator=gen) * 0.1).to(torch.float16)
+    return dict(qweight=qw, qzeros=qz, scales=sc, g_idx=gi, bias=b, bits=bits, group_size=group_size,
+                sym=sym, desc_act=desc_act, K=K, N=N)
+
+
+def random_layer(K, N, bits=4, group_size=128, sym=True, seed=0, device="cpu"):
+    """Random codes (no quantiser): fast way to build LARGE layers for property tests / benchmarks."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    gs = group_size if group_size > 0 else K
+    G = K // gs
+    qw = torch.randint(-(2 ** 31), 2 ** 31 - 1, (K * bits // 32, N), dtype=torch.int32, device=device, generator=gen)
+    if sym:
+        zw = {4: 0x88888888 - (1 << 32), 8: 0x80808080 - (1 << 32)}[bits]
+        qz = torch.full((G, N * bits // 32), zw, dtype=torch.int32, device=device)
+    else:
+        qz = torch.randint(-(2 ** 31), 2 ** 31 - 1, (G, N * bits // 32), dtype=torch.int32, device=device, generator=gen)
+    sc = (torch.rand(G, N, device=device, generator=gen) * 0.01 + 0.005).to(torch.float16)
+    if bits == 8:
+        sc = sc / 16
+    gi = (torch.arange(K, dtype=torch.int32, device=device) // gs)
+    return dict(qweight=qw, qzeros=qz, scales=sc, g_idx=gi, bias=None, bits=bits, group_size=group_size,
+                sym=sym, desc_act=False, K=K, N=N)
+
+
+def oracle_forward(layer, x):
+    xc = x.detach().cpu()
+    return oracle.forward(xc, layer["qweight"].cpu(), layer["qzeros"].cpu(), layer["scales"].cpu().to(
+        torch.float16 if x.dtype == torch.float16 else x.dtype), layer["g_idx"].cpu(), layer["bits"],
+        bias=None if layer["bias"] is None else layer["bias"].cpu())
+
+
+def assert_close_rel(out, ref, rel=1e-3, what=""):
+    """|out - ref| <= rel * |ref| + rel * rms(ref): the north-star's "1e-3 rel fp16" with an absolute floor
+    for outputs that cancel to ~0."""
+    o, r = out.detach().float().cpu(), ref.detach().float().cpu()
+    assert o.shape == r.shape, (o.shape, r.shape)
+    assert torch.isfinite(o).all(), f"{what}: non-finite output"
+    rms = r.pow(2).mean().sqrt().item()
+    err = (o - r).abs()
+    tol = rel * r.abs() + rel * rms
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside {rel:g} rel; max abs err "
+                           f"{err.max().item():.3e}, rms(ref) {rms:.3e}, worst ratio {(err / tol).max().item():.2f}")

@@ -1,0 +1,238 @@
+"""GPU (B200): CUDA path vs the oracle, through the public module AND the raw C-ABI.  pytest -m gpu"""
+import pytest
+import torch
+
+import oracle
+from helpers import assert_close_rel, make_layer, oracle_forward, random_layer
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _module(layer, dtype=None):
+    from gptqmodel_b200 import B200QuantLinear
+    return B200QuantLinear.from_checkpoint_tensors(
+        layer["qweight"], layer["qzeros"], layer["scales"], layer["g_idx"], layer["bits"], layer["group_size"],
+        bias=layer["bias"], desc_act=layer["desc_act"], sym=layer["sym"], device=DEV, dtype=dtype)
+
+
+def _abi_call(fn_name, mod, x, **kw):
+    """Call b2q_gemv / b2q_gemm directly with raw pointers."""
+    import gptqmodel_b200 as g
+    M, K, N = x.shape[0], mod.in_features, mod.out_features
+    out = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    code = 0 if x.dtype == torch.float16 else 1
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    st = torch.cuda.current_stream().cuda_stream
+    if fn_name == "gemv":
+        assert M == 1
+        g.check(g.lib.b2q_gemv(p(x), p(mod.packed), p(mod._scales_for(x.dtype)), p(mod._zeros_dev), p(mod.perm),
+                               p(mod._bias_for(x.dtype)), p(out), K, N, mod.bits, mod.group_size, code,
+                               kw.get("ks", 0), kw.get("warps", 0), st), "b2q_gemv")
+    else:
+        nb = g.lib.b2q_workspace_bytes(max(M, 2), K, N, int(mod.perm is not None))
+        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=x.device)
+        g.check(g.lib.b2q_gemm(p(x), p(mod.packed), p(mod._scales_for(x.dtype)), p(mod._zeros_dev), p(mod.perm),
+                               p(mod._bias_for(x.dtype)), p(out), M, K, N, mod.bits, mod.group_size, code,
+                               p(ws), ws.numel(), st), "b2q_gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_prepack_layout_bit_exact():
+    """B2Q tiles hold exactly the checkpoint's codes (4-bit nibble order {0,2,4,6,1,3,5,7}, 8-bit natural)."""
+    for bits, desc in ((4, False), (4, True), (8, False), (8, True)):
+        L = make_layer(256, 128, bits=bits, group_size=64, sym=False, desc_act=desc, seed=3)
+        mod = _module(L)
+        codes = oracle.unpack_qweight(L["qweight"], bits)  # [K, N]
+        if mod.perm is not None:
+            codes = codes[mod.perm.cpu().long()]
+        raw = mod.packed.cpu().numpy().view("uint32")
+        K, N = 256, 128
+        sub = bits // 4
+        raw = torch.from_numpy(raw.astype("int64")).reshape(K // 32, N // 32, sub, 32, 4)  # [kc][nt][h][lane][word]
+        got = torch.zeros(K, N, dtype=torch.int64)
+        order = [0, 2, 4, 6, 1, 3, 5, 7]
+        for kc in range(K // 32):
+            for nt in range(N // 32):
+                for h in range(sub):
+                    for j in range(4):
+                        w = raw[kc, nt, h, :, j]
+                        if bits == 4:
+                            for i in range(8):
+                                got[kc * 32 + j * 8 + order[i], nt * 32:(nt + 1) * 32] = (w >> (4 * i)) & 0xF
+                        else:
+                            for b in range(4):
+                                got[kc * 32 + h * 16 + j * 4 + b, nt * 32:(nt + 1) * 32] = (w >> (8 * b)) & 0xFF
+        assert torch.equal(got, codes.long()), (bits, desc)
+
+
+def test_q4_reference_golden_vector_on_gpu(q4_golden):
+    """The reference's own KAT (tests/test_q4_exllama_v2.py:32-87 + tests/q4_reference.py), GEMV and GEMM tiers."""
+    torch.manual_seed(42)
+    qweight = torch.randint(-100, 100, size=(128, 1024), dtype=torch.int32)
+    scales = torch.zeros(8, 1024, dtype=torch.float16) + 0.002
+    qzeros = torch.full((8, 128), 0x11111111, dtype=torch.int32)
+    g_idx = torch.arange(1024, dtype=torch.int32) // 128
+    x = torch.rand(1, 1, 1024, dtype=torch.float16)
+    from gptqmodel_b200 import B200QuantLinear
+    mod = B200QuantLinear.from_checkpoint_tensors(qweight, qzeros, scales, g_idx, 4, 128, device=DEV)
+    ref = torch.tensor(q4_golden["reference"], dtype=torch.float16)
+    y = mod(x.to(DEV))[0][0].cpu()
+    assert torch.allclose(y, ref, rtol=3e-5, atol=2e-2)
+    assert (y.float() - ref.float()).abs().max().item() < 8e-3
+    y2 = _abi_call("gemm", mod, x.to(DEV).reshape(1, 1024))[0].cpu()
+    assert torch.allclose(y2, ref, rtol=3e-5, atol=2e-2)
+    assert (y2.float() - ref.float()).abs().max().item() < 8e-3
+
+
+def test_reference_generated_cases(ref_cases):
+    """Fixtures produced by the reference's TorchLinear (tests/golden/make_golden.py)."""
+    from gptqmodel_b200 import B200QuantLinear
+    for name in ref_cases.names():
+        m = ref_cases.meta[name]
+        mod = B200QuantLinear.from_checkpoint_tensors(
+            ref_cases.get(name, "qweight"), ref_cases.get(name, "qzeros"), ref_cases.get(name, "scales"),
+            ref_cases.get(name, "g_idx"), m["bits"], m["group_size"], bias=ref_cases.get(name, "bias"),
+            desc_act=m["desc_act"], sym=m["sym"], device=DEV)
+        x = ref_cases.get(name, "x").to(DEV)
+        y = mod(x)
+        # reference CPU fp16 matmul differs from fp32-accumulate by <= ~1 fp16 ulp
+        assert torch.allclose(y.float().cpu(), ref_cases.get(name, "y_fp16").float(), rtol=2e-3, atol=2e-3), name
+        yo = oracle.forward(x.cpu(), ref_cases.get(name, "qweight"), ref_cases.get(name, "qzeros"),
+                            ref_cases.get(name, "scales"), ref_cases.get(name, "g_idx"), m["bits"],
+                            bias=ref_cases.get(name, "bias"))
+        assert_close_rel(y, yo, 1e-3, name)
+        for i in range(x.shape[0]):  # every row through the GEMV tier as well
+            yi = mod(x[i:i + 1])
+            assert_close_rel(yi, yo[i:i + 1], 1e-3, f"{name} row {i}")
+        ybf = mod(x.to(torch.bfloat16))
+        assert torch.allclose(ybf.float().cpu(), ref_cases.get(name, "y_bf16"), rtol=2e-2, atol=3e-2), name
+
+
+CASES = [
+    # K, N, bits, group, sym, desc_act, bias
+    (256, 512, 4, 128, True, False, False),
+    (256, 512, 4, -1, True, False, False),
+    (256, 512, 4, 64, True, True, False),
+    (256, 512, 4, 128, True, True, True),
+    (1024, 1024, 4, 32, False, False, True),
+    (1024, 1024, 4, 64, False, True, False),
+    (2048, 1024, 4, 128, False, False, False),
+    (512, 256, 8, 128, True, False, False),
+    (512, 256, 8, 32, False, True, True),
+    (1024, 512, 8, 64, False, False, False),
+    (4096, 4096, 4, 128, True, False, False),   # BASELINE configs[0] shape
+    (4096, 1024, 4, 128, True, True, False),    # k/v proj with act-order (config 3)
+    (3584, 4096, 4, 64, False, False, False),   # Mixtral TP-4 w2 shard, g64 asym (config 5)
+    (1024, 96, 4, 128, True, False, False),     # N not a multiple of the 128-feature GEMM tile
+]
+
+
+@pytest.mark.parametrize("K,N,bits,gs,sym,desc,bias", CASES)
+def test_forward_matches_oracle_fp16(K, N, bits, gs, sym, desc, bias):
+    L = make_layer(K, N, bits=bits, group_size=gs, sym=sym, desc_act=desc, bias=bias, seed=42)
+    mod = _module(L)
+    gen = torch.Generator().manual_seed(43)
+    for M in (1, 2, 7, 64, 128, 129, 300):
+        x = (torch.randn(M, K, generator=gen) * 0.5).to(torch.float16)
+        ref = oracle_forward(L, x)
+        out = mod(x.to(DEV))
+        assert out.dtype == torch.float16 and out.shape == (M, N)
+        assert_close_rel(out, ref, 1e-3, f"M={M}")
+    # both tiers directly through the C-ABI on the same row
+    x1 = (torch.randn(1, K, generator=gen) * 0.5).to(torch.float16)
+    ref1 = oracle_forward(L, x1)
+    assert_close_rel(_abi_call("gemv", mod, x1.to(DEV)), ref1, 1e-3, "abi gemv")
+    assert_close_rel(_abi_call("gemm", mod, x1.to(DEV)), ref1, 1e-3, "abi gemm M=1")
+    for ks, warps in ((1, 8), (2, 4), (4, 2), (8, 1), (16, 4)):
+        if 4 * -(-(K // 128) // ks) <= 128 and ks <= K // 128:
+            assert_close_rel(_abi_call("gemv", mod, x1.to(DEV), ks=ks, warps=warps), ref1, 1e-3, f"ks={ks}")
+
+
+@pytest.mark.parametrize("K,N,bits,gs,sym,desc,bias", CASES[:10])
+def test_forward_matches_oracle_bf16(K, N, bits, gs, sym, desc, bias):
+    L = make_layer(K, N, bits=bits, group_size=gs, sym=sym, desc_act=desc, bias=bias, seed=7)
+    L["scales"] = L["scales"].to(torch.bfloat16)  # model loaded in bf16: scales become bf16 (single rounding)
+    if bias:
+        L["bias"] = L["bias"].to(torch.bfloat16)
+    mod = _module(L, dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(44)
+    for M in (1, 5, 130):
+        x = (torch.randn(M, K, generator=gen) * 0.5).to(torch.bfloat16)
+        ref = oracle.forward(x, L["qweight"], L["qzeros"], L["scales"], L["g_idx"], bits, bias=L["bias"])
+        out = mod(x.to(DEV))
+        assert out.dtype == torch.bfloat16
+        assert_close_rel(out, ref, 8e-3, f"bf16 M={M}")  # bf16 budget of tests/kernels/test_gptq.py:353-360
+
+
+def test_batched_and_empty_shapes():
+    L = make_layer(256, 128, seed=5, bias=True)
+    mod = _module(L)
+    x = (torch.randn(2, 3, 256) * 0.5).to(torch.float16)
+    out = mod(x.to(DEV))
+    assert out.shape == (2, 3, 128)
+    assert_close_rel(out.reshape(6, 128), oracle_forward(L, x.reshape(6, 256)), 1e-3)
+    e = mod(torch.zeros(0, 256, dtype=torch.float16, device=DEV))  # qlinear/marlin.py:308-309
+    assert e.shape == (0, 128)
+    xs = torch.randn(4, 512, device=DEV).to(torch.float16)[:, ::2]  # non-contiguous input
+    assert_close_rel(mod(xs), oracle_forward(L, xs.cpu()), 1e-3)
+
+
+def test_nonuniform_g_idx_rejected():
+    L = make_layer(256, 128, group_size=64, seed=5)
+    gi = L["g_idx"].clone()
+    gi[0] = 3  # group 0 loses a row, group 3 gains one
+    L["g_idx"] = gi
+    with pytest.raises(NotImplementedError):
+        _module(L)
+
+
+@pytest.mark.parametrize("K,N", [(4096, 14336), (14336, 4096), (4096, 4096), (4096, 1024)])
+def test_llama3_8b_shapes_full_size(K, N):
+    """BASELINE configs[1] shapes at full size: oracle evaluated on the GPU in fp32 from the same rounded W."""
+    L = random_layer(K, N, bits=4, group_size=128, sym=True, seed=K + N)
+    mod = _module(L)
+    W = oracle.dequantize_weight(L["qweight"].to(DEV), L["qzeros"].to(DEV), L["scales"].to(DEV),
+                                 L["g_idx"].to(DEV), 4).float()
+    torch.manual_seed(1)
+    x = (torch.randn(2048, K, device=DEV) * 0.5).to(torch.float16)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = (x.float() @ W).to(torch.float16)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    out = mod(x)
+    assert_close_rel(out, ref, 1e-3, "prefill M=2048")
+    out1 = mod(x[5:6])
+    assert_close_rel(out1, ref[5:6], 1e-3, "decode M=1")
+    # size-independent properties: determinism and tier agreement
+    assert torch.equal(mod(x[5:6]), out1)
+    assert torch.equal(mod(x), out)
+    lin = mod((x[:8] * 2).to(torch.float16))  # exact scaling by 2 commutes with every rounding step
+    assert torch.equal(lin, (out[:8] * 2))
+
+
+def test_cuda_graph_capture_and_stream():
+    L = make_layer(1024, 512, seed=9)
+    mod = _module(L)
+    x1 = (torch.randn(1, 1024, device=DEV) * 0.5).to(torch.float16)
+    x8 = (torch.randn(8, 1024, device=DEV) * 0.5).to(torch.float16)
+    ref1, ref8 = mod(x1).clone(), mod(x8).clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            mod(x1), mod(x8)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y1 = mod(x1)
+        y8 = mod(x8)
+    x1.copy_(x1 * 0 + x1)  # same values, replays must reproduce
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y1, ref1) and torch.equal(y8, ref8)

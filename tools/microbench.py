@@ -1,0 +1,119 @@
+"""GPU microbenchmarks used while tuning (not the contract bench; see bench.py).
+
+  python tools/microbench.py gemv     sweep split-K cluster size / warps per Llama-3-8B shape (M=1)
+  python tools/microbench.py gemm     time the tcgen05 GEMM at M=2048 per shape
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import gptqmodel_b200 as g  # noqa: E402
+from gptqmodel_b200 import B200QuantLinear  # noqa: E402
+from helpers import random_layer  # noqa: E402
+from oracle import algorithmic_bytes  # noqa: E402
+
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+SHAPES = [(4096, 4096), (4096, 1024), (4096, 14336), (14336, 4096)]
+
+
+def build(K, N, copies, bits=4, gs=128, sym=True):
+    mods = []
+    for c in range(copies):
+        L = random_layer(K, N, bits=bits, group_size=gs, sym=sym, seed=c, device="cuda")
+        mods.append(B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"],
+                                                            bits, gs, device="cuda"))
+    return mods
+
+
+def time_graph(fn, iters=20):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fn()
+    for _ in range(3):
+        gr.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us per graph
+
+
+def gemv():
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    for K, N in SHAPES:
+        nbytes = K * N // 2
+        copies = max(2, int(300e6 // nbytes) + 1)  # rotate > L2 (126 MB) of distinct weights
+        mods = build(K, N, copies)
+        x = (torch.randn(1, K, device="cuda") * 0.5).to(torch.float16)
+        out = torch.empty(1, N, dtype=torch.float16, device="cuda")
+        alg = algorithmic_bytes(K, N, 128, 4, 1)
+        res = []
+        for ks in (0, 1, 2, 4, 8, 16):
+            for warps in ((0,) if ks == 0 else (2, 4, 8)):
+                quads = K // 128
+                if ks > 0 and (4 * -(-quads // ks) > 128 or ks > quads):
+                    continue
+
+                def fn():
+                    st = torch.cuda.current_stream().cuda_stream
+                    for m in mods:
+                        g.check(g.lib.b2q_gemv(p(x), p(m.packed), p(m.scales.data), None, None, None, p(out), K, N,
+                                               4, 128, 0, ks, warps, st), "gemv")
+                try:
+                    us = time_graph(fn) / copies
+                except Exception as e:  # noqa: BLE001
+                    print("fail", K, N, ks, warps, e)
+                    continue
+                res.append((us, ks, warps))
+        res.sort()
+        print(f"GEMV K={K} N={N} alg={alg/1e6:.2f}MB copies={copies}")
+        for us, ks, warps in res[:6]:
+            print(f"   ks={ks:2d} warps={warps} {us:7.2f} us  {alg/us/1e3:7.0f} GB/s  frac={alg/us/1e3/PEAKS['hbm_gbs']:.3f}")
+        heur = [r for r in res if r[1] == 0]
+        if heur:
+            print(f"   heuristic: {heur[0][0]:.2f} us")
+        del mods
+        torch.cuda.empty_cache()
+
+
+def gemm(Ms=(2048,)):
+    for K, N in SHAPES:
+        mods = build(K, N, 2)
+        for M in Ms:
+            x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.float16)
+
+            def fn():
+                for m in mods:
+                    m(x)
+            us = time_graph(fn, iters=10) / len(mods)
+            fl = 2.0 * M * K * N
+            print(f"GEMM M={M} K={K} N={N}: {us:8.1f} us  {fl/us/1e6:7.1f} TFLOP/s  frac={fl/us/1e6/PEAKS['bf16_tflops']:.3f}")
+        W = torch.randn(K, N, device="cuda", dtype=torch.float16)
+        x = (torch.randn(Ms[-1], K, device="cuda") * 0.5).to(torch.float16)
+        us = time_graph(lambda: torch.matmul(x, W), iters=10)
+        print(f"   cuBLAS fp16 dense M={Ms[-1]}: {us:8.1f} us  {2.0*Ms[-1]*K*N/us/1e6:7.1f} TFLOP/s")
+        del mods
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "gemv"
+    if what == "gemv":
+        gemv()
+    elif what == "gemm":
+        gemm(tuple(int(a) for a in sys.argv[2:]) or (2048,))
