@@ -21,6 +21,7 @@ SYMBOLS = {
     "b2q_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b2q_prepack": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b2q_mm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "b2q_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2q_gemv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2q_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b2q_permute_cols": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

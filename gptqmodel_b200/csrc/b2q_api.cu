@@ -1,6 +1,7 @@
 // b2q_api.cu — the extern "C" boundary declared in include/b2q.h: argument validation + tier dispatch.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/b2q.h"
 #include "b2q_internal.h"
@@ -34,8 +35,8 @@ static int validate(const char* fn, const void* x, const void* packed, const voi
     set_error("%s: dtype=%d not supported (0 fp16, 1 bf16)", fn, dtype);
     return -2;
   }
-  if (M < 0 || K <= 0 || N <= 0 || K % 32 != 0 || N % 32 != 0) {
-    set_error("%s: shape M=%d K=%d N=%d not supported (K, N multiples of 32)", fn, M, K, N);
+  if (M < 0 || K <= 0 || N <= 0 || K % 64 != 0 || N % 32 != 0) {
+    set_error("%s: shape M=%d K=%d N=%d not supported (K multiple of 64, N multiple of 32)", fn, M, K, N);
     return -2;
   }
   if (group_size < 32 || group_size % 32 != 0 || K % group_size != 0) {
@@ -72,6 +73,10 @@ static MmArgs make_args(const void* x, const void* packed, const void* scales, c
   a.stream = (cudaStream_t)stream;
   a.tune_ks = 0;
   a.tune_warps = 0;
+  {
+    const char* e = getenv("B2Q_DISABLE_PDL");
+    a.pdl = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
   return a;
 }
 }  // namespace b2q
@@ -96,8 +101,9 @@ int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K
     set_error("b2q_prepack: null pointer argument");
     return -2;
   }
-  if ((bits != 4 && bits != 8) || K <= 0 || N <= 0 || K % 32 != 0 || N % 32 != 0) {
-    set_error("b2q_prepack: bits=%d K=%d N=%d not supported (bits 4|8, K and N multiples of 32)", bits, K, N);
+  if ((bits != 4 && bits != 8) || K <= 0 || N <= 0 || K % 64 != 0 || N % 32 != 0) {
+    set_error("b2q_prepack: bits=%d K=%d N=%d not supported (bits 4|8, K multiple of 64, N multiple of 32)", bits, K,
+              N);
     return -2;
   }
   return check_cuda(launch_prepack(qweight, perm, packed, K, N, bits, (cudaStream_t)stream), "b2q_prepack");
@@ -125,7 +131,31 @@ int b2q_gemv(const void* x, const void* packed, const void* scales, const int32_
                        stream);
   a.tune_ks = ks;
   a.tune_warps = warps;
-  return check_cuda(launch_gemv(a), "b2q_gemv");
+  if (decode_supported(a)) return check_cuda(launch_decode(a), "b2q_gemv(decode)");
+  if (bits == 8 && K % 128 == 0) return check_cuda(launch_gemv(a), "b2q_gemv");
+  set_error("b2q_gemv: no M=1 tier for bits=%d K=%d group_size=%d (use b2q_mm)", bits, K, group_size);
+  return -2;
+}
+
+int b2q_decode(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+               const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, int ks,
+               int warps, void* stream) {
+  int v = validate("b2q_decode", x, packed, scales, out, M, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (ks > 16 || warps > 8 || (ks > 0 && (ks & (ks - 1)) != 0)) {
+    set_error("b2q_decode: ks=%d (power of two <= 16) / warps=%d (<= 8) out of range", ks, warps);
+    return -2;
+  }
+  MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, nullptr, 0,
+                       stream);
+  a.tune_ks = ks;
+  a.tune_warps = warps;
+  if (!decode_supported(a)) {
+    set_error("b2q_decode: needs bits=4, 1 <= M <= 8, K %% 128 == 0, group_size 64|128|K (got bits=%d M=%d K=%d g=%d)",
+              bits, M, K, group_size);
+    return -2;
+  }
+  return check_cuda(launch_decode(a), "b2q_decode");
 }
 
 int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
@@ -147,7 +177,8 @@ int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t*
   if (M == 0) return 0;
   MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
                        workspace_bytes, stream);
-  if (M == 1) return check_cuda(launch_gemv(a), "b2q_mm(gemv)");
+  if (decode_supported(a)) return check_cuda(launch_decode(a), "b2q_mm(decode)");
+  if (M == 1 && bits == 8 && K % 128 == 0) return check_cuda(launch_gemv(a), "b2q_mm(gemv)");
   return check_cuda(launch_gemm(a), "b2q_mm(gemm)");
 }
 

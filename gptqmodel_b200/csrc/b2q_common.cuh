@@ -1,17 +1,23 @@
 // b2q_common.cuh — shared device helpers for the B200 (sm_100a) GPTQ QuantLinear kernels.
 //
-// Prepacked weight layout ("B2Q tiles", produced by b2q_prepack.cu from the checkpoint layout
+// Prepacked weight layouts ("B2Q tiles", produced by b2q_prepack.cu from the checkpoint layout
 // qweight int32 [K*bits/32, N] of /root/reference/gptqmodel/nn_modules/qlinear/__init__.py:827-865):
 //
-//   4-bit:  uint4 T[K/32][N/32][32]        one uint4 = 32 consecutive k of ONE output feature n
-//   8-bit:  uint4 T[K/32][N/32][2][32]     one uint4 = 16 consecutive k of ONE output feature n
+//   4-bit:  uint4 T4[K/64][N/16][32]      one warp-wide 512-byte row = 16 output features x 64 k
+//   8-bit:  uint4 T8[K/32][N/32][2][32]   one uint4 = 16 consecutive k of ONE output feature n
 //
-// so a warp reading T[kc][nt][*] issues one fully coalesced 512-byte request (32 features x 32 k), and a
-// CTA tile of 128 features x 32 k is one contiguous 2 KB (4-bit) block for cp.async.bulk.
-// Inside a 4-bit 32-bit word (8 consecutive k: k0..k7) the nibble at bits [4i,4i+4) holds k-offset
-// {0,2,4,6,1,3,5,7}[i], so that  (w & 0x000f000f)|0x64006400 = half2(1024+k0, 1024+k1),
-// (w & 0x00f000f0)|0x64006400 = half2(1024+16*k2, 1024+16*k3), and the same on (w >> 8) gives k4..k7:
-// K-consecutive half2 pairs with one LOP3 each (no PRMT), ready for a 16-byte K-major smem store.
+// 4-bit ("fragment-major"): lane = 4*g + t (g = 0..7, t = 0..3) owns features 16*ft+g and 16*ft+g+8 and the 16
+// consecutive k  64*kb + 16*t .. +15.  Word s (0..3) of its uint4 covers k = 64*kb + 16*t + 4*s + {0,1,2,3};
+// inside a word the nibble at bits [4p, 4p+4) holds
+//      p = 0,4 : feature g   , k+0, k+1        p = 1,5 : feature g+8 , k+0, k+1
+//      p = 2,6 : feature g   , k+2, k+3        p = 3,7 : feature g+8 , k+2, k+3
+// so that  (w & 0x000f000f)|0x64006400 = half2(1024+q) of (g, k+0..1),   (w & 0x00f000f0)|0x64006400 =
+// half2(1024+16q) of (g+8, k+0..1), and the same two masks on (w >> 8) give k+2..3: FOUR LOP3 (+1 shift) turn a
+// word into the four A-operand registers of one mma.sync.m16n8k16 (decode tier: rows g / g+8, the k permutation is
+// shared with the activation fragment), and the same registers are K-consecutive pairs of ONE feature row, so the
+// tcgen05 GEMM tier stores them as 16-byte K-major shared-memory chunks.  Rows g carry the magic bias 1024, rows g+8
+// carry 16*(64+q): one bias class per output row, removed once per group with the activation sum.
+// A CTA tile of 128 features x 64 k is ONE contiguous 4 KB block for cp.async.bulk.
 // With act-order the rows are first sorted by group (k' -> original row perm[k']) so groups are contiguous.
 #pragma once
 #include <cuda_fp16.h>
@@ -215,7 +221,7 @@ struct ET<__half> {
   static constexpr float LO_BASE = 1024.f;        // nibble in mantissa bits [0,4)
   static constexpr float HI_BASE = 64.f;          // nibble in mantissa bits [4,8): (1024+16q)/16 = 64+q
   static constexpr float HI_SCALE = 0.0625f;
-  // one 32-bit word (8 consecutive k) -> 4 packed pairs (k0,k1) (k2,k3) (k4,k5) (k6,k7);
+  // one 32-bit word -> 4 packed pairs: h[0] = (g, k0..1), h[1] = (g+8, k0..1), h[2] = (g, k2..3), h[3] = (g+8, k2..3)
   // h[0], h[2] = LO_BASE + q ; h[1], h[3] = (HI_BASE + q) / HI_SCALE      (all exact)
   __device__ static __forceinline__ void unpack_w4(uint32_t w, uint32_t (&h)[4]) {
     h[0] = lop3_and_or(w, 0x000f000fu, MAGIC);

@@ -30,8 +30,8 @@ struct GemmCfg {
   static constexpr int SUB = BITS / 4;
   static constexpr int A_BYTES = MT * 128 * G_BK * 2;
   static constexpr int B_BYTES = G_BN * G_BK * 2;
-  static constexpr int P_CHUNK_BYTES = 4 * SUB * 512;  // 4 feature tiles x 32 k
-  static constexpr int P_BYTES = 2 * P_CHUNK_BYTES;    // 2 k-chunks per 64-k block
+  static constexpr int P_CHUNK_BYTES = 4 * SUB * 512;  // 8-bit: 4 feature tiles (of 32) x 32 k
+  static constexpr int P_BYTES = 2 * P_CHUNK_BYTES;    // 128 features x 64 k (4-bit: one 4 KB T4 row block)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + P_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
@@ -61,49 +61,67 @@ __device__ __forceinline__ SZRaw load_sz(const T* __restrict__ scales, const uin
 template <typename T, int BITS>
 struct Dequant;
 
+// 4-bit fragment-major uint4 (see b2q_common.cuh): features (g, g+8) x 16 consecutive k.
+// lo[c] / hi[c] = 8 consecutive k (chunk c = 0,1 of the lane's 16) of feature g / g+8, exactly (q - z) * s.
 template <>
 struct Dequant<__half, 4> {
-  // z: integer zero point.  returns 4 x uint4 (32 halves)
-  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[4]) {
-    const uint32_t s2u = s16 | (s16 << 16);
-    const __half2 s2 = *reinterpret_cast<const __half2*>(&s2u);
-    const __half2 zlo = __float2half2_rn(1024.f + (float)z);   // exact
-    const __half2 zhi = __float2half2_rn(-(64.f + (float)z));  // exact
+  __device__ static __forceinline__ void run(const uint4& pv, uint32_t slo16, int zlo_i, uint32_t shi16, int zhi_i,
+                                             uint4 (&lo)[2], uint4 (&hi)[2]) {
+    const uint32_t slu = slo16 | (slo16 << 16), shu = shi16 | (shi16 << 16);
+    const __half2 sl = *reinterpret_cast<const __half2*>(&slu), sh = *reinterpret_cast<const __half2*>(&shu);
+    const __half2 zlo = __float2half2_rn(1024.f + (float)zlo_i);  // exact
+    const __half2 zhi = __float2half2_rn(-(64.f + (float)zhi_i));  // exact
     const __half2 sixteenth = __float2half2_rn(0.0625f);
     const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+    uint32_t l[8], u[8];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int s4 = 0; s4 < 4; ++s4) {
       uint32_t h[4];
-      ET<__half>::unpack_w4(w[t], h);
-      __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[0]), zlo), s2);
-      __half2 v1 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[1]), sixteenth, zhi), s2);
-      __half2 v2 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[2]), zlo), s2);
-      __half2 v3 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[3]), sixteenth, zhi), s2);
-      o[t] = make_uint4(*reinterpret_cast<uint32_t*>(&v0), *reinterpret_cast<uint32_t*>(&v1),
-                        *reinterpret_cast<uint32_t*>(&v2), *reinterpret_cast<uint32_t*>(&v3));
+      ET<__half>::unpack_w4(w[s4], h);
+      __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[0]), zlo), sl);
+      __half2 v1 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[1]), sixteenth, zhi), sh);
+      __half2 v2 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[2]), zlo), sl);
+      __half2 v3 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[3]), sixteenth, zhi), sh);
+      l[2 * s4] = *reinterpret_cast<uint32_t*>(&v0);
+      l[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v2);
+      u[2 * s4] = *reinterpret_cast<uint32_t*>(&v1);
+      u[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v3);
     }
+    lo[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    lo[1] = make_uint4(l[4], l[5], l[6], l[7]);
+    hi[0] = make_uint4(u[0], u[1], u[2], u[3]);
+    hi[1] = make_uint4(u[4], u[5], u[6], u[7]);
   }
 };
 
 template <>
 struct Dequant<__nv_bfloat16, 4> {
-  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[4]) {
-    const uint32_t s2u = s16 | (s16 << 16);
-    const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s2u);
-    const __nv_bfloat162 zb = __float2bfloat162_rn(128.f + (float)z);  // exact (<= 143)
+  __device__ static __forceinline__ void run(const uint4& pv, uint32_t slo16, int zlo_i, uint32_t shi16, int zhi_i,
+                                             uint4 (&lo)[2], uint4 (&hi)[2]) {
+    const uint32_t slu = slo16 | (slo16 << 16), shu = shi16 | (shi16 << 16);
+    const __nv_bfloat162 sl = *reinterpret_cast<const __nv_bfloat162*>(&slu);
+    const __nv_bfloat162 sh = *reinterpret_cast<const __nv_bfloat162*>(&shu);
+    const __nv_bfloat162 zl = __float2bfloat162_rn(128.f + (float)zlo_i);  // exact (<= 143)
+    const __nv_bfloat162 zh = __float2bfloat162_rn(128.f + (float)zhi_i);
     const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+    uint32_t l[8], u[8];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int s4 = 0; s4 < 4; ++s4) {
       uint32_t h[4];
-      ET<__nv_bfloat16>::unpack_w4(w[t], h);
-      uint32_t r[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 v = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[i]), zb), s2);
-        r[i] = *reinterpret_cast<uint32_t*>(&v);
-      }
-      o[t] = make_uint4(r[0], r[1], r[2], r[3]);
+      ET<__nv_bfloat16>::unpack_w4(w[s4], h);
+      __nv_bfloat162 v0 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[0]), zl), sl);
+      __nv_bfloat162 v1 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[1]), zh), sh);
+      __nv_bfloat162 v2 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[2]), zl), sl);
+      __nv_bfloat162 v3 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[3]), zh), sh);
+      l[2 * s4] = *reinterpret_cast<uint32_t*>(&v0);
+      l[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v2);
+      u[2 * s4] = *reinterpret_cast<uint32_t*>(&v1);
+      u[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v3);
     }
+    lo[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    lo[1] = make_uint4(l[4], l[5], l[6], l[7]);
+    hi[0] = make_uint4(u[0], u[1], u[2], u[3]);
+    hi[1] = make_uint4(u[4], u[5], u[6], u[7]);
   }
 };
 
@@ -197,20 +215,27 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   if (warp == 0) {
     // ================================ producer ================================
     if (lane == 0) {
-      const uint32_t pbytes = (uint32_t)ntiles * C::SUB * 512u;
+      // 4-bit: the 128 x 64 tile is one contiguous block of T4 (8 feature tiles of 16); 8-bit: two T8 rows
+      const int FT = N >> 4, ft0 = n0 >> 4;
+      const uint32_t pbytes4 = (uint32_t)min(8, FT - ft0) * 512u;
+      const uint32_t pbytes8 = (uint32_t)ntiles * C::SUB * 512u;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_full + 8 * s, C::A_BYTES + 2 * pbytes);
+        mbar_expect_tx(bar_full + 8 * s, C::A_BYTES + (BITS == 4 ? pbytes4 : 2 * pbytes8));
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
           tma_load_2d(sA + s * C::A_BYTES + mt * (128 * G_BK * 2), &tmap_x, bar_full + 8 * s, kb * G_BK,
                       m0 + mt * 128);
+        if (BITS == 4) {
+          bulk_load(sP + s * C::P_BYTES, packed + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_full + 8 * s);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          bulk_load(sP + s * C::P_BYTES + j * C::P_CHUNK_BYTES,
-                    packed + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes, bar_full + 8 * s);
+          for (int j = 0; j < 2; ++j)
+            bulk_load(sP + s * C::P_BYTES + j * C::P_CHUNK_BYTES,
+                      packed + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes8, bar_full + 8 * s);
+        }
       }
     }
   } else if (warp == 1) {
@@ -239,46 +264,87 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     }
   } else {
     // ================================ dequant warps ================================
-    const int t = threadIdx.x - 64;  // feature row inside the tile
-    const int n = n0 + t;
-    const bool nvalid = n < N;
-    const int nsafe = nvalid ? n : 0;
-    const int ntl = t >> 5;
+    const int t = threadIdx.x - 64;  // 0..127
     constexpr int PF = 32 / BITS;
     constexpr int ZSYM = 1 << (BITS - 1);
     const int gchunks = group_size >> 5;  // 32-k chunks per group
-    // software-pipelined scale/zero fetch: [j] for the two 32-k chunks of a block
-    SZRaw cur[2], nxt[2];
-    cur[0] = load_sz<T, BITS, ASYM>(scales, qzeros, 0, nsafe, N);
-    cur[1] = load_sz<T, BITS, ASYM>(scales, qzeros, 1 / gchunks, nsafe, N);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      if (kb + 1 < nkb) {
-        nxt[0] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2) / gchunks, nsafe, N);
-        nxt[1] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 3) / gchunks, nsafe, N);
-      }
-      mbar_wait(bar_full + 8 * s, ph);
-      const uint32_t brow = sB + s * C::B_BYTES + t * 128;
-      const uint32_t sw = (uint32_t)(t & 7);
+    if (BITS == 4) {
+      // thread owns two fragment-major uint4 per stage: feature tiles (t>>5) and (t>>5)+4, lane' = t&31 = 4g+tt
+      const int lp = t & 31, g = lp >> 2, tt = lp & 3;
+      int f[4];  // tile-local feature rows: lo/hi of the two uint4
+      f[0] = (t >> 5) * 16 + g;
+      f[1] = f[0] + 8;
+      f[2] = f[0] + 64;
+      f[3] = f[0] + 72;
+      int nf[4];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        int z = ZSYM;
-        if (ASYM) z = (int)((cur[j].zw >> (BITS * (nsafe % PF))) & ((1u << BITS) - 1));
-        const uint4* pj = reinterpret_cast<const uint4*>(smem + (sP - smem_base) + s * C::P_BYTES +
-                                                         j * C::P_CHUNK_BYTES);
-        if (BITS == 4) {
-          const uint4 pv = pj[ntl * 32 + lane];
-          uint4 o[4];
-          Dequant<T, 4>::run(pv, cur[j].s, z, o);
+      for (int i = 0; i < 4; ++i) nf[i] = (n0 + f[i] < N) ? n0 + f[i] : 0;
+      // this lane's 16 k of block kb lie in 32-k chunk 2*kb + (tt>>1)
+      SZRaw cur[4], nxt[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t addr = brow + (((uint32_t)(j * 4 + c) ^ sw) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[c].x), "r"(o[c].y),
-                         "r"(o[c].z), "r"(o[c].w)
+      for (int i = 0; i < 4; ++i) cur[i] = load_sz<T, BITS, ASYM>(scales, qzeros, (tt >> 1) / gchunks, nf[i], N);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        if (kb + 1 < nkb) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            nxt[i] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2 + (tt >> 1)) / gchunks, nf[i], N);
+        }
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint4* pj = reinterpret_cast<const uint4*>(smem + (sP - smem_base) + s * C::P_BYTES);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint4 pv = pj[t + u * 128];
+          int zl = ZSYM, zh = ZSYM;
+          if (ASYM) {
+            zl = (int)((cur[2 * u].zw >> (4 * g)) & 15u);      // (n0 + f) % 8 == g for both rows
+            zh = (int)((cur[2 * u + 1].zw >> (4 * g)) & 15u);
+          }
+          uint4 lo[2], hi[2];
+          Dequant<T, 4>::run(pv, cur[2 * u].s, zl, cur[2 * u + 1].s, zh, lo, hi);
+          const uint32_t sw = (uint32_t)g;  // (row & 7) for rows f and f+8
+          const uint32_t rlo = sB + s * C::B_BYTES + f[2 * u] * 128;
+          const uint32_t rhi = rlo + 8 * 128;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t off = (((uint32_t)(2 * tt + c)) ^ sw) << 4;
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rlo + off), "r"(lo[c].x), "r"(lo[c].y),
+                         "r"(lo[c].z), "r"(lo[c].w)
+                         : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rhi + off), "r"(hi[c].x), "r"(hi[c].y),
+                         "r"(hi[c].z), "r"(hi[c].w)
                          : "memory");
           }
-        } else {
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_bready + 8 * s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      }
+    } else {
+      const int n = n0 + t;
+      const int nsafe = (n < N) ? n : 0;
+      const int ntl = t >> 5;
+      SZRaw cur[2], nxt[2];
+      cur[0] = load_sz<T, BITS, ASYM>(scales, qzeros, 0, nsafe, N);
+      cur[1] = load_sz<T, BITS, ASYM>(scales, qzeros, 1 / gchunks, nsafe, N);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        if (kb + 1 < nkb) {
+          nxt[0] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2) / gchunks, nsafe, N);
+          nxt[1] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 3) / gchunks, nsafe, N);
+        }
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint32_t brow = sB + s * C::B_BYTES + t * 128;
+        const uint32_t sw = (uint32_t)(t & 7);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          int z = ZSYM;
+          if (ASYM) z = (int)((cur[j].zw >> (BITS * (nsafe % PF))) & ((1u << BITS) - 1));
+          const uint4* pj = reinterpret_cast<const uint4*>(smem + (sP - smem_base) + s * C::P_BYTES +
+                                                           j * C::P_CHUNK_BYTES);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint4 pv = pj[(ntl * 2 + h) * 32 + lane];
@@ -293,11 +359,11 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             }
           }
         }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_bready + 8 * s);
+        cur[0] = nxt[0];
+        cur[1] = nxt[1];
       }
-      fence_proxy_async_smem();
-      mbar_arrive(bar_bready + 8 * s);
-      cur[0] = nxt[0];
-      cur[1] = nxt[1];
     }
 
     // ================================ epilogue ================================

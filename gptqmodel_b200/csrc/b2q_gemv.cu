@@ -22,15 +22,22 @@ namespace b2q {
 constexpr int GEMV_MAX_WARPS = 8;
 constexpr int GEMV_MAX_CPC = 128;  // chunks (of 32 k) per CTA  -> 8 KB of staged activations
 
-template <typename T, int BITS>
+template <typename T, int BITS, bool ASYM>
 struct Quad {
   uint4 v[4 * (BITS / 4)];
+  uint16_t s[4];   // raw scale of the group each chunk belongs to
+  uint32_t zw[4];  // packed zero-point word (ASYM only)
 };
 
-template <typename T, int BITS>
-__device__ __forceinline__ void load_quad(Quad<T, BITS>& q, const uint4* __restrict__ packed, int kc, int c1, int NT,
-                                          int nt, int lane) {
+// Issue every global load one quad (4 chunks = 128 k of one feature) needs: 4 (8) x LDG.128 of packed weights
+// plus the per-group scale / zero words, so nothing on the critical path waits for a dependent load later.
+template <typename T, int BITS, bool ASYM>
+__device__ __forceinline__ void load_quad(Quad<T, BITS, ASYM>& q, const uint4* __restrict__ packed,
+                                          const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, int kc,
+                                          int c1, int NT, int nt, int lane, int gchunks, int N) {
   constexpr int SUB = BITS / 4;
+  constexpr int PF = 32 / BITS;
+  const int n = nt * 32 + lane;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -39,6 +46,17 @@ __device__ __forceinline__ void load_quad(Quad<T, BITS>& q, const uint4* __restr
         q.v[j * SUB + h] = ldg_nc_v4(packed + (((size_t)(kc + j) * NT + nt) * SUB + h) * 32 + lane);
       else
         q.v[j * SUB + h] = make_uint4(0, 0, 0, 0);
+    }
+    if (kc + j < c1 && (j == 0 || (kc + j) % gchunks == 0)) {
+      const int g = (kc + j) / gchunks;
+      q.s[j] = *reinterpret_cast<const uint16_t*>(scales + (size_t)g * N + n);
+      if (ASYM) q.zw[j] = qzeros[(size_t)g * (N / PF) + n / PF];
+    } else if (j > 0) {
+      q.s[j] = q.s[j - 1];
+      if (ASYM) q.zw[j] = q.zw[j - 1];
+    } else {
+      q.s[j] = 0;
+      if (ASYM) q.zw[j] = 0;
     }
   }
 }
@@ -119,42 +137,68 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32)
   constexpr float LO_BASE = (BITS == 8 && E::FMT == 1) ? 0.f : (BITS == 8 ? 1024.f : E::LO_BASE);
   constexpr float HI_BASE = E::HI_BASE;
 
-  // ---- 1. first weight quad in flight before anything else -------------------------------------
+  // ---- 1. first weight quad (+ its scales) in flight before anything else ----------------------
+  const int gchunks = group_size >> 5;  // chunks per group (>= 1)
   int q = c0 + warp * 4;
-  Quad<T, BITS> cur;
-  load_quad<T, BITS>(cur, packed, q, c1, NT, nt, lane);
+  Quad<T, BITS, ASYM> cur;
+  load_quad<T, BITS, ASYM>(cur, packed, scales, qzeros, q, c1, NT, nt, lane, gchunks, N);
 
-  // ---- 2. stage activations (with the act-order gather fused) + per-chunk sums -----------------
-  const int nk = (c1 - c0) * 32;
-  if (PERM) {
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) sx[i] = x[perm[c0 * 32 + i]];
-  } else {
-    const uint4* xg = reinterpret_cast<const uint4*>(x + (size_t)c0 * 32);
+  // Programmatic dependent launch: the weights above never depend on the previous kernel in the stream,
+  // the activations do.  Let the NEXT kernel start prefetching its weights now, and wait for the PREVIOUS
+  // kernel's output (our x) only here.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- 2. stage activations (act-order gather fused) and reduce the per-chunk sums in one pass --
+  //   thread i owns 8 consecutive k (one uint4); 4 neighbouring lanes own one 32-k chunk.
+  {
+    const int n4 = (c1 - c0) * 4;                 // uint4 slots of valid activations
+    const int n4r = (n4 + 31) & ~31;              // whole warps take part in the shuffles
     uint4* xsm = reinterpret_cast<uint4*>(sx);
-    for (int i = threadIdx.x; i < nk / 8; i += blockDim.x) xsm[i] = xg[i];
-  }
-  __syncthreads();
-  for (int cc = warp; cc < c1 - c0; cc += nwarps) {
-    const float v = E::to_f(sx[cc * 32 + lane]);
-    // 4-bit: k%8 in {2,3,6,7} are the "hi" magic class (see unpack_w4)
-    const bool is_hi = (BITS == 4) && (lane & 2);
-    float lo = is_hi ? 0.f : v, hi = is_hi ? v : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo += __shfl_xor_sync(0xffffffffu, lo, o);
-      hi += __shfl_xor_sync(0xffffffffu, hi, o);
+    for (int i = threadIdx.x; i < n4r; i += blockDim.x) {
+      uint4 xv = make_uint4(0, 0, 0, 0);
+      if (i < n4) {
+        if (PERM) {
+          const int4* pp = reinterpret_cast<const int4*>(perm + (size_t)c0 * 32) + 2 * i;
+          const int4 p0 = pp[0], p1 = pp[1];
+          const uint16_t* xu = reinterpret_cast<const uint16_t*>(x);
+          xv.x = (uint32_t)xu[p0.x] | ((uint32_t)xu[p0.y] << 16);
+          xv.y = (uint32_t)xu[p0.z] | ((uint32_t)xu[p0.w] << 16);
+          xv.z = (uint32_t)xu[p1.x] | ((uint32_t)xu[p1.y] << 16);
+          xv.w = (uint32_t)xu[p1.z] | ((uint32_t)xu[p1.w] << 16);
+        } else {
+          xv = reinterpret_cast<const uint4*>(x + (size_t)c0 * 32)[i];
+        }
+        xsm[i] = xv;
+      }
+      // pairs .x/.z are the "lo" magic class (k%8 in {0,1,4,5}), .y/.w the "hi" class (4-bit only)
+      auto f2 = [](uint32_t u) {
+        const T* h = reinterpret_cast<const T*>(&u);
+        return E::to_f(h[0]) + E::to_f(h[1]);
+      };
+      float lo, hi;
+      if (BITS == 4) {
+        lo = f2(xv.x) + f2(xv.z);
+        hi = f2(xv.y) + f2(xv.w);
+      } else {
+        lo = (f2(xv.x) + f2(xv.z)) + (f2(xv.y) + f2(xv.w));
+        hi = 0.f;
+      }
+      lo += __shfl_xor_sync(0xffffffffu, lo, 1);
+      hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+      lo += __shfl_xor_sync(0xffffffffu, lo, 2);
+      hi += __shfl_xor_sync(0xffffffffu, hi, 2);
+      if ((i & 3) == 0 && i < n4) csum[i >> 2] = make_float2(lo, hi);
     }
-    if (lane == 0) csum[cc] = make_float2(lo, hi);
   }
   __syncthreads();
 
   // ---- 3. main loop: one quad (4 chunks = 128 k) per iteration, next quad prefetched -----------
   float total = 0.f;
-  const int gshift_chunks = group_size >> 5;  // chunks per group (>= 1)
   while (q < c1) {
     const int qn = q + nwarps * 4;
-    Quad<T, BITS> nxt;
-    if (qn < c1) load_quad<T, BITS>(nxt, packed, qn, c1, NT, nt, lane);
+    Quad<T, BITS, ASYM> nxt;
+    if (qn < c1) load_quad<T, BITS, ASYM>(nxt, packed, scales, qzeros, qn, c1, NT, nt, lane, gchunks, N);
     float lo = 0.f, hi = 0.f, cl = 0.f, ch = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -164,15 +208,14 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32)
         const float2 cs = csum[kc - c0];
         cl += cs.x;
         ch += cs.y;
-        const bool group_end = ((kc + 1) % gshift_chunks == 0) || (kc + 1 == c1) || (j == 3);
+        const bool group_end = ((kc + 1) % gchunks == 0) || (kc + 1 == c1) || (j == 3);
         if (group_end) {
-          const int g = kc / gshift_chunks;
-          const float s = E::to_f(scales[(size_t)g * N + n]);
+          const uint16_t sraw = cur.s[j];
+          const float s = E::to_f(*reinterpret_cast<const T*>(&sraw));
           float z = ZSYM;
           if (ASYM) {
             constexpr int PF = 32 / BITS;
-            const uint32_t zw = qzeros[(size_t)g * (N / PF) + n / PF];
-            z = (float)((zw >> (BITS * (n % PF))) & ((1u << BITS) - 1));
+            z = (float)((cur.zw[j] >> (BITS * (n % PF))) & ((1u << BITS) - 1));
           }
           const float dot = lo + hi * E::HI_SCALE - ((LO_BASE + z) * cl + (HI_BASE + z) * ch);
           total = fmaf(s, dot, total);
@@ -212,13 +255,15 @@ static int launch_gemv_t(const MmArgs& a, int ks, int warps, int cpc) {
   cfg.blockDim = dim3(warps * 32, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = a.stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = ks;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL, see the kernel prologue
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = a.pdl ? 2 : 1;
   auto kern = gemv_kernel<T, BITS, ASYM, PERM>;
   if (ks > 8) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -247,6 +292,10 @@ static void gemv_config(const MmArgs& a, int& ks, int& warps, int& cpc) {
 }
 
 int launch_gemv(const MmArgs& a) {
+  if (a.bits != 8) {
+    set_error("b2q_gemv(FHFMA): only the 8-bit T8 layout is handled here; 4-bit uses the decode tier");
+    return -1;
+  }
   int ks, warps, cpc;
   gemv_config(a, ks, warps, cpc);
   if (cpc > GEMV_MAX_CPC) {
@@ -259,8 +308,8 @@ int launch_gemv(const MmArgs& a) {
                 : launch_gemv_t<T, BITS, true, false>(a, ks, warps, cpc))             \
         : (perm ? launch_gemv_t<T, BITS, false, true>(a, ks, warps, cpc)              \
                 : launch_gemv_t<T, BITS, false, false>(a, ks, warps, cpc)))
-  if (a.dtype == 0) return a.bits == 4 ? B2Q_GEMV_CASE(__half, 4) : B2Q_GEMV_CASE(__half, 8);
-  return a.bits == 4 ? B2Q_GEMV_CASE(__nv_bfloat16, 4) : B2Q_GEMV_CASE(__nv_bfloat16, 8);
+  if (a.dtype == 0) return B2Q_GEMV_CASE(__half, 8);
+  return B2Q_GEMV_CASE(__nv_bfloat16, 8);
 #undef B2Q_GEMV_CASE
 }
 

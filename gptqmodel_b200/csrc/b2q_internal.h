@@ -22,11 +22,14 @@ struct MmArgs {
   cudaStream_t stream;
   int tune_ks;     // >0: force GEMV cluster size (split-K)
   int tune_warps;  // >0: force GEMV warps per CTA
+  int pdl;         // 1: launch with programmatic stream serialization (default)
 };
 
 int launch_prepack(const void* qweight, const int32_t* perm, void* out, int K, int N, int bits, cudaStream_t stream);
 int launch_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, cudaStream_t stream);
-int launch_gemv(const MmArgs& a);
+int launch_gemv(const MmArgs& a);     // 8-bit, M == 1: CUDA-core FHFMA GEMV
+int launch_decode(const MmArgs& a);   // 4-bit, M <= 8: mma.sync decode tier
+bool decode_supported(const MmArgs& a);
 int launch_gemm(const MmArgs& a);
 void set_error(const char* fmt, ...);
 

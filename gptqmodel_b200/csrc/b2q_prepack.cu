@@ -10,18 +10,47 @@
 
 namespace b2q {
 
-template <int BITS>
-__global__ void prepack_kernel(const uint32_t* __restrict__ qweight, const int32_t* __restrict__ perm,
-                               uint4* __restrict__ out, int K, int N) {
-  constexpr int SUB = BITS / 4;  // uint4 per (chunk, feature): 1 for 4-bit, 2 for 8-bit
+// 4-bit: T4[K/64][N/16][32] fragment-major (see b2q_common.cuh)
+__global__ void prepack4_kernel(const uint32_t* __restrict__ qweight, const int32_t* __restrict__ perm,
+                                uint4* __restrict__ out, int K, int N) {
+  const int FT = N / 16;
+  const long long total = (long long)(K / 64) * FT * 32;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int lane = (int)(idx & 31);
+  const long long rest = idx >> 5;
+  const int ft = (int)(rest % FT);
+  const int kb = (int)(rest / FT);
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t w[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int koff = ((p & 2) ? 2 : 0) + (p >> 2);
+      const int n = ft * 16 + g + ((p & 1) ? 8 : 0);
+      const int kp = kb * 64 + t * 16 + s * 4 + koff;
+      const int k = perm ? perm[kp] : kp;
+      const uint32_t q = (qweight[(size_t)(k >> 3) * N + n] >> (4 * (k & 7))) & 0xFu;
+      word |= q << (4 * p);
+    }
+    w[s] = word;
+  }
+  out[idx] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 8-bit: T8[K/32][N/32][2][32], natural byte order
+__global__ void prepack8_kernel(const uint32_t* __restrict__ qweight, const int32_t* __restrict__ perm,
+                                uint4* __restrict__ out, int K, int N) {
   const int NT = N / 32;
-  const long long total = (long long)(K / 32) * NT * SUB * 32;
+  const long long total = (long long)(K / 32) * NT * 2 * 32;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int lane = (int)(idx & 31);
   long long rest = idx >> 5;
-  const int h = (int)(rest % SUB);
-  rest /= SUB;
+  const int h = (int)(rest % 2);
+  rest /= 2;
   const int nt = (int)(rest % NT);
   const int kc = (int)(rest / NT);
   const int n = nt * 32 + lane;
@@ -29,24 +58,12 @@ __global__ void prepack_kernel(const uint32_t* __restrict__ qweight, const int32
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t word = 0;
-    if (BITS == 4) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // nibble position i holds k-offset {0,2,4,6,1,3,5,7}[i]
-        const int koff = (i < 4) ? (2 * i) : (2 * (i - 4) + 1);
-        const int kp = kc * 32 + j * 8 + koff;
-        const int k = perm ? perm[kp] : kp;
-        const uint32_t q = (qweight[(size_t)(k >> 3) * N + n] >> (4 * (k & 7))) & 0xFu;
-        word |= q << (4 * i);
-      }
-    } else {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int kp = kc * 32 + h * 16 + j * 4 + b;
-        const int k = perm ? perm[kp] : kp;
-        const uint32_t q = (qweight[(size_t)(k >> 2) * N + n] >> (8 * (k & 3))) & 0xFFu;
-        word |= q << (8 * b);
-      }
+    for (int b = 0; b < 4; ++b) {
+      const int kp = kc * 32 + h * 16 + j * 4 + b;
+      const int k = perm ? perm[kp] : kp;
+      const uint32_t q = (qweight[(size_t)(k >> 2) * N + n] >> (8 * (k & 3))) & 0xFFu;
+      word |= q << (8 * b);
     }
     w[j] = word;
   }
@@ -55,13 +72,16 @@ __global__ void prepack_kernel(const uint32_t* __restrict__ qweight, const int32
 
 int launch_prepack(const void* qweight, const int32_t* perm, void* out, int K, int N, int bits,
                    cudaStream_t stream) {
-  const long long total = (long long)(K / 32) * (N / 32) * (bits / 4) * 32;
   const int threads = 256;
-  const long long blocks = (total + threads - 1) / threads;
-  if (bits == 4)
-    prepack_kernel<4><<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)qweight, perm, (uint4*)out, K, N);
-  else
-    prepack_kernel<8><<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)qweight, perm, (uint4*)out, K, N);
+  if (bits == 4) {
+    const long long total = (long long)(K / 64) * (N / 16) * 32;
+    prepack4_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+        (const uint32_t*)qweight, perm, (uint4*)out, K, N);
+  } else {
+    const long long total = (long long)(K / 32) * (N / 32) * 2 * 32;
+    prepack8_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+        (const uint32_t*)qweight, perm, (uint4*)out, K, N);
+  }
   return (int)cudaGetLastError();
 }
 

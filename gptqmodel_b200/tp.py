@@ -1,0 +1,107 @@
+"""Tensor-parallel sharding of GPTQ QuantLinear checkpoint tensors + the row-parallel all-reduce.
+
+The reference has no tensor-parallel code; the rules below are the ones it documents for the
+engines it delegates to: scales of a row-parallel act-order layer must be replicated on all ranks
+(`marlin_repeat_scales_on_all_ranks`, gptqmodel/utils/marlin.py:300-305), K shards must be whole groups
+(`marlin_is_k_full` :296-297, TensorParallelPadderConfig quantization/config.py:1184-1188).
+
+  column-parallel (q,k,v,gate,up / expert w1,w3): rank r owns output features [r*N/P, (r+1)*N/P)  -> no comm
+  row-parallel    (o_proj, down_proj / expert w2): rank r owns input rows    [r*K/P, (r+1)*K/P)  -> partial sums,
+                  ONE all-reduce(sum) of the [M, N] output per layer; bias is added on rank 0 only.
+
+All functions work on checkpoint-layout tensors on any device (they are pure slicing), so the host logic is
+testable with the gloo backend on CPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+Layer = Dict[str, object]
+
+
+def _check(layer: Layer):
+    for k in ("qweight", "qzeros", "scales", "g_idx", "bits", "group_size"):
+        if k not in layer:
+            raise KeyError(f"layer dict misses {k!r}")
+
+
+def shard_columns(layer: Layer, rank: int, world: int) -> Layer:
+    """Column-parallel shard: slice the N axis of qweight / scales / qzeros (qzeros packs 32/bits columns/word)."""
+    _check(layer)
+    bits = int(layer["bits"])
+    pf = 32 // bits
+    qweight, qzeros, scales = layer["qweight"], layer["qzeros"], layer["scales"]
+    N = qweight.shape[1]
+    if N % world != 0 or (N // world) % 32 != 0:
+        raise NotImplementedError(f"column shard: N={N} / {world} must be a multiple of 32")
+    n0, n1 = rank * N // world, (rank + 1) * N // world
+    out = dict(layer)
+    out["qweight"] = qweight[:, n0:n1].contiguous()
+    out["scales"] = scales[:, n0:n1].contiguous()
+    out["qzeros"] = qzeros[:, n0 // pf:n1 // pf].contiguous()
+    out["g_idx"] = layer["g_idx"].clone()
+    if layer.get("bias") is not None:
+        out["bias"] = layer["bias"][n0:n1].contiguous()
+    out["N"] = n1 - n0
+    return out
+
+
+def shard_rows(layer: Layer, rank: int, world: int) -> Layer:
+    """Row-parallel shard: slice the K axis.  Needs K/P to be whole groups and a group-contiguous g_idx."""
+    _check(layer)
+    bits = int(layer["bits"])
+    pf = 32 // bits
+    qweight, qzeros, scales, g_idx = layer["qweight"], layer["qzeros"], layer["scales"], layer["g_idx"]
+    K = g_idx.shape[0]
+    gs = int(layer["group_size"])
+    gs = gs if gs > 0 else K
+    if K % world != 0:
+        raise NotImplementedError(f"row shard: K={K} not divisible by {world}")
+    k0, k1 = rank * K // world, (rank + 1) * K // world
+    if int(layer["group_size"]) <= 0 and world > 1:
+        # one group spans all of K: every rank keeps the single scale row
+        g0, g1 = 0, 1
+    else:
+        if (k1 - k0) % gs != 0:
+            raise NotImplementedError(f"row shard: K/P={k1 - k0} must be a multiple of group_size={gs}")
+        g0, g1 = k0 // gs, k1 // gs
+    trivial = torch.equal(g_idx.to(torch.int64).cpu(), torch.arange(K) // gs)
+    if not trivial:
+        raise NotImplementedError(
+            "row-parallel shard of an act-order layer: scales would have to be replicated and groups are no longer "
+            "whole inside a shard (marlin_repeat_scales_on_all_ranks); not supported by the B2Q tile layout yet")
+    out = dict(layer)
+    out["qweight"] = qweight[k0 // pf:k1 // pf].contiguous()
+    out["scales"] = scales[g0:g1].contiguous()
+    out["qzeros"] = qzeros[g0:g1].contiguous()
+    if int(layer["group_size"]) <= 0:
+        out["g_idx"] = torch.zeros(k1 - k0, dtype=torch.int32, device=g_idx.device)
+        out["group_size"] = -1
+    else:
+        out["g_idx"] = (g_idx[k0:k1] - g0).to(torch.int32).contiguous()
+    if layer.get("bias") is not None:
+        out["bias"] = layer["bias"] if rank == 0 else None  # added once, before the reduce
+    out["K"] = k1 - k0
+    return out
+
+
+def all_reduce_sum_(t: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """The single collective of a row-parallel QuantLinear: in-place sum over the TP group (NCCL on GPUs)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class RowParallelLinear(torch.nn.Module):
+    """Wraps a row-sharded QuantLinear: forward(x_shard) -> all-reduced full output."""
+
+    def __init__(self, inner: torch.nn.Module, group: Optional[dist.ProcessGroup] = None):
+        super().__init__()
+        self.inner = inner
+        self.group = group
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return all_reduce_sum_(self.inner(x), self.group)

@@ -46,11 +46,11 @@ size_t b2q_packed_bytes(int K, int N, int bits);
 size_t b2q_workspace_bytes(int M, int K, int N, int has_perm);
 
 /* Repack checkpoint-layout qweight into B2Q tiles.  perm (int32 [K], k' -> original row) may be NULL.
- * Requires K % 32 == 0, N % 32 == 0, bits in {4, 8}. */
+ * Requires K % 64 == 0, N % 32 == 0, bits in {4, 8}. */
 int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K, int N, int bits, void* stream);
 
-/* out[M, N] = x[M, K] @ dequant(W) (+ bias).  Dispatches on M inside the library (M == 1: cluster split-K GEMV,
- * otherwise the tcgen05 GEMM) so a CUDA graph sees the true M.
+/* out[M, N] = x[M, K] @ dequant(W) (+ bias).  Dispatches on M inside the library (M <= 8: cluster split-K decode
+ * tier, otherwise the tcgen05 GEMM) so a CUDA graph sees the true M.
  *   x, scales, bias, out : fp16 (dtype 0) or bf16 (dtype 1), all the same type; x and out contiguous row-major
  *   qzeros               : NULL for symmetric layers (zero-point 2^(bits-1)), else int32 [G, N*bits/32]
  *   perm                 : NULL, or int32 [K] act-order permutation used at prepack
@@ -60,7 +60,14 @@ int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t*
            const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
            size_t workspace_bytes, void* stream);
 
-/* The two tiers individually (tests, benchmarks, tuning).  b2q_gemv requires M == 1; ks/warps <= 0 = heuristic. */
+/* The tiers individually (tests, benchmarks, tuning); ks (split-K cluster size) / warps <= 0 = heuristic.
+ *   b2q_decode : 4-bit, 1 <= M <= 8, K % 128 == 0, group_size 64|128|K: fragment-major weights -> mma.sync, per-group
+ *                fix-up, cluster split-K reduced through distributed shared memory (the bs=1 decode path)
+ *   b2q_gemv   : M == 1 (routes 4-bit to b2q_decode, 8-bit to the CUDA-core fma.rn.f32.f16 GEMV)
+ *   b2q_gemm   : any M, the tcgen05 + TMA tensor-core tier */
+int b2q_decode(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+               const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, int ks,
+               int warps, void* stream);
 int b2q_gemv(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
              const void* bias, void* out, int K, int N, int bits, int group_size, int dtype, int ks, int warps,
              void* stream);
