@@ -103,10 +103,14 @@ class ClockSampler(threading.Thread):
 def synth_layer(K, N, seed, device, bits=4, gs=128):
     """Random int4 codes + scales sized so activations stay O(1) through the 224-layer chain (sym, zero=8)."""
     gen = torch.Generator(device=device).manual_seed(seed)
-    qw = torch.randint(-(2 ** 31), 2 ** 31 - 1, (K * bits // 32, N), dtype=torch.int32, device=device, generator=gen)
+    # codes uniform in 1..15: zero-mean around the symmetric zero-point 8 (a non-zero weight mean would be amplified
+    # ~sqrt(K) per layer and overflow fp16 after a few of the 224 chained layers)
+    qw = torch.zeros((K * bits // 32, N), dtype=torch.int32, device=device)
+    for j in range(8):
+        qw |= torch.randint(1, 16, (K // 8, N), dtype=torch.int32, device=device, generator=gen) << (4 * j)
     G = K // gs
     qz = torch.full((G, N * bits // 32), 0x88888888 - (1 << 32), dtype=torch.int32, device=device)
-    base = 1.0 / (21.25 * K) ** 0.5  # var(q-8) = 21.25 for uniform codes
+    base = 1.0 / (18.67 * K) ** 0.5  # var(q-8) = 18.67 for codes uniform in 1..15
     sc = ((0.8 + 0.4 * torch.rand(G, N, device=device, generator=gen)) * base).to(torch.float16)
     gi = torch.arange(K, dtype=torch.int32, device=device) // gs
     return dict(qweight=qw, qzeros=qz, scales=sc, g_idx=gi, bias=None, bits=bits, group_size=gs)

@@ -87,6 +87,8 @@ extern "C" {
 
 int b2q_version(void) { return B2Q_ABI_VERSION; }
 
+void b2q_debug_set_trace(void* device_buffer) { g_trace_ptr = device_buffer; }
+
 const char* b2q_last_error(void) { return g_err; }
 
 size_t b2q_packed_bytes(int K, int N, int bits) { return (size_t)K * (size_t)N * (size_t)bits / 8; }
@@ -123,8 +125,8 @@ int b2q_gemv(const void* x, const void* packed, const void* scales, const int32_
              void* stream) {
   int v = validate("b2q_gemv", x, packed, scales, out, 1, K, N, bits, group_size, dtype);
   if (v != 0) return v;
-  if (ks > 16 || warps > 8 || (ks > 0 && (ks & (ks - 1)) != 0)) {
-    set_error("b2q_gemv: ks=%d (power of two <= 16) / warps=%d (<= 8) out of range", ks, warps);
+  if (ks > 16 || warps > 16 || (ks > 0 && (ks & (ks - 1)) != 0)) {
+    set_error("b2q_gemv: ks=%d (power of two <= 16) / warps=%d (<= 16) out of range", ks, warps);
     return -2;
   }
   MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, 1, K, N, bits, group_size, dtype, nullptr, 0,
@@ -142,8 +144,8 @@ int b2q_decode(const void* x, const void* packed, const void* scales, const int3
                int warps, void* stream) {
   int v = validate("b2q_decode", x, packed, scales, out, M, K, N, bits, group_size, dtype);
   if (v != 0) return v;
-  if (ks > 16 || warps > 8 || (ks > 0 && (ks & (ks - 1)) != 0)) {
-    set_error("b2q_decode: ks=%d (power of two <= 16) / warps=%d (<= 8) out of range", ks, warps);
+  if (ks > 16 || warps > 16 || (ks > 0 && (ks & (ks - 1)) != 0)) {
+    set_error("b2q_decode: ks=%d (power of two <= 16) / warps=%d (<= 16) out of range", ks, warps);
     return -2;
   }
   MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, nullptr, 0,

@@ -24,7 +24,7 @@
 
 namespace b2q {
 
-constexpr int DEC_MAX_WARPS = 8;
+constexpr int DEC_MAX_WARPS = 16;
 constexpr int DEC_MAXM = 8;
 
 template <typename T>
@@ -44,24 +44,23 @@ __device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&d)[4], const ui
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// One "quad" = 128 k x 32 features = 4 coalesced 512-byte rows of T4 (2 k-blocks of 64 x 2 feature tiles of 16),
-// plus the scale / zero words of the (up to 2) groups it touches, for the 4 feature rows this lane owns.
+// One "quad" = 128 k x 32 features = two contiguous 1 KB pieces of T4 (k-blocks 2q and 2q+1, feature tiles 2nt and
+// 2nt+1).  Each warp owns a private ring of DEC_STAGES quad buffers in shared memory, filled by cp.async.bulk
+// (UBLKCP) and tracked by one mbarrier per stage: up to DEC_STAGES * 2 KB per warp are in flight with no register
+// cost, which is what keeps > 100 KB per SM outstanding (the first, register-prefetch version of this kernel kept
+// 2 KB per warp in flight and topped out at ~3 TB/s incremental: profiles/r01_decode_notes.md).
+constexpr int DEC_STAGES = 4;
+constexpr int DEC_QUAD_BYTES = 2048;
+
 template <bool ASYM, bool G64>
-struct DQuad {
-  uint4 v[4];                  // [kbl * 2 + ftl]
+struct DScale {
   uint16_t s[G64 ? 2 : 1][4];  // [group in quad][ftl * 2 + hi]
   uint32_t zw[(ASYM ? 1 : 0) * (G64 ? 2 : 1) + (ASYM ? 0 : 1)][4];
 };
 
 template <typename T, bool ASYM, bool G64>
-__device__ __forceinline__ void load_dquad(DQuad<ASYM, G64>& q, const uint4* __restrict__ wp, size_t kb_stride,
-                                           const T* __restrict__ scales, const uint32_t* __restrict__ qzeros,
-                                           int quad, int gsh, int N, int nrow0) {
-  // wp already points at (kb = 2*quad, ft = 2*nt, lane)
-  q.v[0] = ldg_nc_v4(wp);
-  q.v[1] = ldg_nc_v4(wp + 32);
-  q.v[2] = ldg_nc_v4(wp + kb_stride);
-  q.v[3] = ldg_nc_v4(wp + kb_stride + 32);
+__device__ __forceinline__ void load_dscale(DScale<ASYM, G64>& q, const T* __restrict__ scales,
+                                            const uint32_t* __restrict__ qzeros, int quad, int gsh, int N, int nrow0) {
   const int g0 = (quad * 2) >> gsh;  // group of k-block 2*quad   (gsh = log2(group_size / 64), 31 for per-channel)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -79,41 +78,78 @@ __device__ __forceinline__ void load_dquad(DQuad<ASYM, G64>& q, const uint4* __r
   }
 }
 
+__device__ __forceinline__ void issue_quad(uint32_t dst, uint32_t bar, const uint4* __restrict__ src,
+                                           size_t kb_stride) {
+  mbar_expect_tx(bar, DEC_QUAD_BYTES);
+  bulk_load(dst, src, 1024, bar);                     // k-block 2q   : feature tiles 2nt, 2nt+1
+  bulk_load(dst + 1024, src + kb_stride, 1024, bar);  // k-block 2q+1
+}
+
+// Persistent-style CTA: blockIdx.x strides over the 32-feature tiles (tile = blockIdx.x + i * gridDim.x), blockIdx.y is
+// the split-K rank inside the cluster.  x is staged ONCE per CTA; the warps split the k-quads of every tile; each
+// warp's bulk-copy ring runs ahead across tile boundaries.
 template <typename T, bool ASYM, bool G64>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     decode_kernel(const uint4* __restrict__ packed, const T* __restrict__ scales, const uint32_t* __restrict__ qzeros,
                   const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ bias,
-                  T* __restrict__ out, int M, int K, int N, int gsh, int qpc) {
+                  T* __restrict__ out, int M, int K, int N, int gsh, int qpc, int max_tiles,
+                  unsigned long long* __restrict__ trace) {
   using E = ET<T>;
-  extern __shared__ __align__(16) uint8_t dsm[];
-  // dynamic smem: sx[M][kspan] (T) | xsum[kblocks][8] (float) | red[nwarps][8 acc][32] | part[8][32]
+  extern __shared__ __align__(128) uint8_t dsm[];
+  // optional phase timestamps (debug): trace[blockIdx.x * 16 + slot] = %globaltimer (ns)
+  auto stamp = [&](int slot) {
+    if (trace != nullptr && threadIdx.x == 0 && blockIdx.y == 0) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      trace[blockIdx.x * 16 + slot] = tns;
+    }
+  };
+  stamp(0);
+  // dynamic smem: ring[nwarps][DEC_STAGES][2 KB] | sx[M][kspan] (T) | xsum[kblocks][8] | red[2][nwarps][8][32] |
+  //               part[max_tiles][8][32] | mbarriers[nwarps][DEC_STAGES]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int nt = blockIdx.x, FT = N >> 4;
+  const int NT = N >> 5, FT = N >> 4, C = gridDim.x;
+  const int ntiles = (blockIdx.x < NT) ? (NT - blockIdx.x + C - 1) / C : 0;  // tiles of this CTA
   const int nquads = K >> 7;
   const int q0 = blockIdx.y * qpc;
   const int q1 = min(q0 + qpc, nquads);
   const int kspan = qpc * 128;
-  T* sx = reinterpret_cast<T*>(dsm);
-  float* xsum = reinterpret_cast<float*>(dsm + (size_t)M * kspan * sizeof(T));
+  uint8_t* ring = dsm + (size_t)warp * DEC_STAGES * DEC_QUAD_BYTES;
+  T* sx = reinterpret_cast<T*>(dsm + (size_t)nwarps * DEC_STAGES * DEC_QUAD_BYTES);
+  float* xsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sx) + (size_t)M * kspan * sizeof(T));
   float* red = xsum + qpc * 2 * 8;
-  float* part = red + nwarps * 8 * 32;
+  float* part = red + 2 * nwarps * 256;
+  const uint32_t bars = smem_u32(part + max_tiles * 256) + warp * DEC_STAGES * 8;
   const bool PERM = perm != nullptr;
-  const int nrow0 = nt * 32 + g;       // this lane's first feature row (others: +8, +16, +24)
   const size_t kb_stride = (size_t)FT * 32;
 
-  // ---- 1. first quad of weights (+ scales) in flight before anything else ----------------------
-  int q = q0 + warp;
-  DQuad<ASYM, G64> cur;
-  const uint4* wbase = packed + ((size_t)nt * 2) * 32 + lane;
-  if (q < q1)
-    load_dquad<T, ASYM, G64>(cur, wbase + (size_t)(2 * q) * kb_stride, kb_stride, scales, qzeros, q, gsh, N, nrow0);
+  // ---- 1. the first DEC_STAGES quads of this warp requested before anything else -----------------
+  const int nq = (q0 + warp < q1) ? (q1 - q0 - warp + nwarps - 1) / nwarps : 0;  // quads per tile for this warp
+  const int U = ntiles * nq;                                                     // units of this warp
+  auto unit_src = [&](int u) {
+    const int ti = u / nq, qi = u - ti * nq;
+    const int nt = blockIdx.x + ti * C, q = q0 + warp + qi * nwarps;
+    return packed + ((size_t)(2 * q) * FT + 2 * nt) * 32;
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < DEC_STAGES; ++i) mbar_init(bars + 8 * i, 1);
+    fence_mbar_init();
+#pragma unroll
+    for (int i = 0; i < DEC_STAGES; ++i)
+      if (i < U) issue_quad(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i, unit_src(i), kb_stride);
+  }
+  DScale<ASYM, G64> cur;
+  if (U > 0) load_dscale<T, ASYM, G64>(cur, scales, qzeros, q0 + warp, gsh, N, blockIdx.x * 32 + g);
 
   // PDL: let the next kernel start its own weight prefetch; wait for the producer of x only now.
+  stamp(1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  stamp(2);
 
-  // ---- 2. stage x[m, k-range] (act-order gather fused) + per-(64 k block, token) sums ----------
+  // ---- 2. stage x[m, k-range] (act-order gather fused) + per-(64 k block, token) sums, ONCE ------
   {
     const int n8 = (q1 - q0) * 16;   // uint4 (8 halves) per token row in this CTA's k-range
     const int tot = M * n8;
@@ -153,147 +189,222 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       if ((i & 7) >= M) xsum[i] = 0.f;
   }
   __syncthreads();
+  stamp(3);
 
-  // ---- 3. main loop ----------------------------------------------------------------------------
+  // ---- 3. loop over this CTA's tiles; inside a tile the warps split the k-quads --------------------
   constexpr float ZSYM = 8.f;
-  float tot[2][4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) tot[a][b] = 0.f;
-
-  while (q < q1) {
-    const int qn = q + nwarps;
-    DQuad<ASYM, G64> nxt;
-    if (qn < q1)
-      load_dquad<T, ASYM, G64>(nxt, wbase + (size_t)(2 * qn) * kb_stride, kb_stride, scales, qzeros, qn, gsh, N,
-                               nrow0);
-    float d[2][4];
+  const uint32_t nrank = cluster_nctarank();
+  int u = 0;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int nt = blockIdx.x + ti * C;
+    float tot[2][4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) d[a][b] = 0.f;
-    float xs0 = 0.f, xs1 = 0.f;  // sum_k x for token columns 2t, 2t+1 over the current group
-#pragma unroll
-    for (int kbl = 0; kbl < 2; ++kbl) {
-      // activation fragment: token (column) g, k = 64*kb + 16t .. +15  -> 8 registers, 2 per k-step
-      uint32_t bx[8];
-      if (g < M) {
-        const uint4* xp = reinterpret_cast<const uint4*>(sx + (size_t)g * kspan + ((q - q0) * 2 + kbl) * 64 + t * 16);
-        const uint4 x0 = xp[0], x1 = xp[1];
-        bx[0] = x0.x; bx[1] = x0.y; bx[2] = x0.z; bx[3] = x0.w;
-        bx[4] = x1.x; bx[5] = x1.y; bx[6] = x1.z; bx[7] = x1.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bx[i] = 0u;
+      for (int b = 0; b < 4; ++b) tot[a][b] = 0.f;
+
+    for (int qi = 0; qi < nq; ++qi, ++u) {
+      const int ql = warp + qi * nwarps;  // quad index relative to q0
+      DScale<ASYM, G64> nxt;
+      if (u + 1 < U) {
+        const int last = (qi + 1 == nq);
+        load_dscale<T, ASYM, G64>(nxt, scales, qzeros, last ? q0 + warp : q0 + ql + nwarps, gsh, N,
+                                  (last ? nt + C : nt) * 32 + g);
       }
+      const int st = u % DEC_STAGES;
+      mbar_wait(bars + 8 * st, (uint32_t)(u / DEC_STAGES) & 1u);
+      const uint4* wq = reinterpret_cast<const uint4*>(ring + st * DEC_QUAD_BYTES) + lane;
+      float dd[2][2][4];  // [kbl][ftl][c]: four independent mma accumulator chains
 #pragma unroll
-      for (int ftl = 0; ftl < 2; ++ftl) {
-        const uint4 wv = cur.v[kbl * 2 + ftl];
-        const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          uint32_t a[4];
-          E::unpack_w4(w[s], a);
-          mma_16816<T>(d[ftl], a, bx[2 * s], bx[2 * s + 1]);
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dd[a][b][c] = 0.f;
+      float xs0 = 0.f, xs1 = 0.f;  // sum_k x for token columns 2t, 2t+1 over the current group
+#pragma unroll
+      for (int kbl = 0; kbl < 2; ++kbl) {
+        // activation fragment: token (column) g, k = 64*kb + 16t .. +15  -> 8 registers, 2 per k-step
+        uint32_t bx[8];
+        if (g < M) {
+          const uint4* xp = reinterpret_cast<const uint4*>(sx + (size_t)g * kspan + (ql * 2 + kbl) * 64 + t * 16);
+          const uint4 x0 = xp[0], x1 = xp[1];
+          bx[0] = x0.x; bx[1] = x0.y; bx[2] = x0.z; bx[3] = x0.w;
+          bx[4] = x1.x; bx[5] = x1.y; bx[6] = x1.z; bx[7] = x1.w;
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) bx[r] = 0u;
         }
-      }
-      const float2 xs = *reinterpret_cast<const float2*>(xsum + ((q - q0) * 2 + kbl) * 8 + 2 * t);
-      xs0 += xs.x;
-      xs1 += xs.y;
-      if (kbl == 1 || G64) {
-        // group boundary: fold the raw accumulators into the output with the per-(group, feature) scale / zero
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int gi = G64 ? kbl : 0;  // compile-time after unrolling
 #pragma unroll
         for (int ftl = 0; ftl < 2; ++ftl) {
-          const uint16_t slr = cur.s[gi][ftl * 2], shr = cur.s[gi][ftl * 2 + 1];
-          const float sl = E::to_f(*reinterpret_cast<const T*>(&slr));
-          const float sh = E::to_f(*reinterpret_cast<const T*>(&shr));
-          float zl = ZSYM, zh = ZSYM;
-          if (ASYM) {
-            zl = (float)((cur.zw[ASYM ? gi : 0][ftl * 2] >> (4 * g)) & 15u);  // feature % 8 == g for all four rows
-            zh = (float)((cur.zw[ASYM ? gi : 0][ftl * 2 + 1] >> (4 * g)) & 15u);
+          const uint4 wv = wq[(kbl * 2 + ftl) * 32];
+          const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            uint32_t a[4];
+            E::unpack_w4(w[s], a);
+            mma_16816<T>(dd[kbl][ftl], a, bx[2 * s], bx[2 * s + 1]);
           }
-          const float bl = E::LO_BASE + zl, bh = E::HI_BASE + zh;
-          tot[ftl][0] = fmaf(sl, d[ftl][0] - bl * xs0, tot[ftl][0]);
-          tot[ftl][1] = fmaf(sl, d[ftl][1] - bl * xs1, tot[ftl][1]);
-          tot[ftl][2] = fmaf(sh, d[ftl][2] * E::HI_SCALE - bh * xs0, tot[ftl][2]);
-          tot[ftl][3] = fmaf(sh, d[ftl][3] * E::HI_SCALE - bh * xs1, tot[ftl][3]);
-          d[ftl][0] = d[ftl][1] = d[ftl][2] = d[ftl][3] = 0.f;
         }
-        xs0 = xs1 = 0.f;
+        const float2 xs = *reinterpret_cast<const float2*>(xsum + (ql * 2 + kbl) * 8 + 2 * t);
+        xs0 += xs.x;
+        xs1 += xs.y;
+        if (kbl == 1 || G64) {
+          // group boundary: fold the raw accumulators into the output with the per-(group, feature) scale / zero
+          const int gi = G64 ? kbl : 0;  // compile-time after unrolling
+#pragma unroll
+          for (int ftl = 0; ftl < 2; ++ftl) {
+            const uint16_t slr = cur.s[gi][ftl * 2], shr = cur.s[gi][ftl * 2 + 1];
+            const float sl = E::to_f(*reinterpret_cast<const T*>(&slr));
+            const float sh = E::to_f(*reinterpret_cast<const T*>(&shr));
+            float zl = ZSYM, zh = ZSYM;
+            if (ASYM) {
+              zl = (float)((cur.zw[ASYM ? gi : 0][ftl * 2] >> (4 * g)) & 15u);  // feature % 8 == g for all rows
+              zh = (float)((cur.zw[ASYM ? gi : 0][ftl * 2 + 1] >> (4 * g)) & 15u);
+            }
+            const float bl = E::LO_BASE + zl, bh = E::HI_BASE + zh;
+            float d[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) d[c] = G64 ? dd[kbl][ftl][c] : dd[0][ftl][c] + dd[1][ftl][c];
+            tot[ftl][0] = fmaf(sl, d[0] - bl * xs0, tot[ftl][0]);
+            tot[ftl][1] = fmaf(sl, d[1] - bl * xs1, tot[ftl][1]);
+            tot[ftl][2] = fmaf(sh, d[2] * E::HI_SCALE - bh * xs0, tot[ftl][2]);
+            tot[ftl][3] = fmaf(sh, d[3] * E::HI_SCALE - bh * xs1, tot[ftl][3]);
+          }
+          xs0 = xs1 = 0.f;
+        }
       }
+      // recycle the stage for unit u + DEC_STAGES (all lanes have finished reading it)
+      __syncwarp();
+      if (lane == 0 && u + DEC_STAGES < U)
+        issue_quad(smem_u32(ring) + st * DEC_QUAD_BYTES, bars + 8 * st, unit_src(u + DEC_STAGES), kb_stride);
+      if (u + 1 < U) cur = nxt;
     }
-    if (qn < q1) cur = nxt;
-    q = qn;
-  }
 
-  // ---- 4. reduce: warps -> CTA (smem) -> cluster (DSMEM) -> global -------------------------------
-  // tot[ftl][c]: feature nt*32 + ftl*16 + g (+8 if c >= 2), token 2t + (c & 1)
+    // ---- tile epilogue: warps -> CTA through (double-buffered) smem, one barrier per tile ---------
+    // tot[ftl][c]: feature nt*32 + ftl*16 + g (+8 if c >= 2), token 2t + (c & 1)
+    if (ti < 5) stamp(4 + 2 * ti);
+    float* rbuf = red + (ti & 1) * nwarps * 256;
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) red[(warp * 8 + a * 4 + b) * 32 + lane] = tot[a][b];
-  __syncthreads();
-  const uint32_t nrank = cluster_nctarank();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    float v = 0.f;
-    for (int w = 0; w < nwarps; ++w) v += red[w * 256 + i];
-    part[i] = v;
-  }
-  if (nrank > 1) cluster_sync_all(); else __syncthreads();
-  if (cluster_ctarank() == 0) {
+      for (int b = 0; b < 4; ++b) rbuf[(warp * 8 + a * 4 + b) * 32 + lane] = tot[a][b];
+    __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-      const int acc = i >> 5, ln = i & 31;
-      const int m = 2 * (ln & 3) + (acc & 1);
-      if (m < M) {
-        float v = part[i];
-        for (uint32_t r = 1; r < nrank; ++r) v += ld_dsmem_f32(smem_u32(&part[i]), r);
-        const int n = nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
-        // reference order: round the matmul to the output dtype, then add bias (qlinear/torch.py:337-342)
-        T o = E::from_f(v);
-        if (bias != nullptr) o = E::from_f(E::to_f(o) + E::to_f(bias[n]));
-        out[(size_t)m * N + n] = o;
+      float v = 0.f;
+      for (int w = 0; w < nwarps; ++w) v += rbuf[w * 256 + i];
+      if (nrank > 1) {
+        part[ti * 256 + i] = v;
+      } else {
+        const int acc = i >> 5, ln = i & 31;
+        const int m = 2 * (ln & 3) + (acc & 1);
+        if (m < M) {
+          const int n = nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
+          // reference order: round the matmul to the output dtype, then add bias (qlinear/torch.py:337-342)
+          T o = E::from_f(v);
+          if (bias != nullptr) o = E::from_f(E::to_f(o) + E::to_f(bias[n]));
+          out[(size_t)m * N + n] = o;
+        }
+      }
+    }
+    if (ti < 5) stamp(5 + 2 * ti);
+  }
+  stamp(15);
+
+  // ---- 4. split-K: the cluster ranks share the tiles of the final DSMEM reduction -----------------
+  if (nrank > 1) {
+    cluster_sync_all();
+    const uint32_t rank = cluster_ctarank();
+    for (int ti = (int)rank; ti < ntiles; ti += (int)nrank) {
+      const int nt = blockIdx.x + ti * C;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int acc = i >> 5, ln = i & 31;
+        const int m = 2 * (ln & 3) + (acc & 1);
+        if (m < M) {
+          float v = 0.f;
+          for (uint32_t r = 0; r < nrank; ++r) v += ld_dsmem_f32(smem_u32(&part[ti * 256 + i]), r);
+          const int n = nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
+          T o = E::from_f(v);
+          if (bias != nullptr) o = E::from_f(E::to_f(o) + E::to_f(bias[n]));
+          out[(size_t)m * N + n] = o;
+        }
+      }
+    }
+    cluster_sync_all();  // keep every rank's smem alive until all peers have read it
+  }
+}
+
+void* g_trace_ptr = nullptr;
+
+struct DecodeCfg {
+  int C, ks, warps, qpc, max_tiles;
+  size_t smem;
+};
+
+static size_t decode_smem(int M, int warps, int qpc, int max_tiles) {
+  return (size_t)warps * DEC_STAGES * DEC_QUAD_BYTES + (size_t)M * qpc * 128 * 2 + (size_t)qpc * 2 * 8 * 4 +
+         (size_t)2 * warps * 256 * 4 + (size_t)max_tiles * 256 * 4 + (size_t)warps * DEC_STAGES * 8;
+}
+
+// Pick (C tiles-columns, ks split-K ranks, warps) minimising the critical path in "quads per warp" on ~148 CTAs.
+static bool decode_config(const MmArgs& a, DecodeCfg& best) {
+  const int quads = a.K / 128, NT = a.N / 32;
+  const int SMS = 148;
+  double best_cost = 1e30;
+  bool found = false;
+  for (int ks = 1; ks <= 8; ks *= 2) {
+    if (a.tune_ks > 0 && ks != a.tune_ks) continue;
+    if (ks > quads) break;
+    const int qpc = (quads + ks - 1) / ks;
+    for (int warps = 4; warps <= DEC_MAX_WARPS; warps *= 2) {  // 4, 8, 16
+      if (a.tune_warps > 0 && warps != a.tune_warps) continue;
+      int C = SMS / ks;
+      if (C > NT) C = NT;
+      if (C < 1) C = 1;
+      const int max_tiles = (NT + C - 1) / C;
+      const size_t smem = decode_smem(a.M, warps, qpc, ks > 1 ? max_tiles : 0);
+      if (smem > 200 * 1024) continue;
+      const int qpw = (qpc + warps - 1) / warps;          // quads per warp per tile
+      // critical path: tiles * quads-per-warp, plus a per-tile barrier and a fixed per-kernel part
+      const double cost = (double)max_tiles * (qpw + 0.35) + (ks > 1 ? 1.5 : 0.0) + (warps == 4 ? 0.3 * max_tiles * qpw : 0.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = DecodeCfg{C, ks, warps, qpc, ks > 1 ? max_tiles : 0, smem};
+        found = true;
       }
     }
   }
-  if (nrank > 1) cluster_sync_all();  // keep peers' smem alive until rank 0 has read it
+  return found;
 }
 
 template <typename T, bool ASYM, bool G64>
-static int launch_decode_t(const MmArgs& a, int ks, int warps, int qpc) {
-  const size_t smem = (size_t)a.M * qpc * 128 * 2 + (size_t)qpc * 2 * 8 * 4 + (size_t)warps * 8 * 32 * 4 + 8 * 32 * 4;
+static int launch_decode_t(const MmArgs& a, const DecodeCfg& c) {
   auto kern = decode_kernel<T, ASYM, G64>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (c.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return (int)e;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(a.N / 32, ks, 1);
-  cfg.blockDim = dim3(warps * 32, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(c.C, c.ks, 1);
+  cfg.blockDim = dim3(c.warps * 32, 1, 1);
+  cfg.dynamicSmemBytes = c.smem;
   cfg.stream = a.stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = ks;
+  attr[0].val.clusterDim.y = c.ks;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = a.pdl ? 2 : 1;
-  if (ks > 8) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return (int)e;
-  }
   int gsh = 31;  // per-channel: every k-block is group 0
   if (a.group_size == 64) gsh = 0;
   else if (a.group_size == 128) gsh = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const uint4*)a.packed, (const T*)a.scales,
                                      (const uint32_t*)a.qzeros, a.perm, (const T*)a.x, (const T*)a.bias, (T*)a.out,
-                                     a.M, a.K, a.N, gsh, qpc);
+                                     a.M, a.K, a.N, gsh, c.qpc, c.max_tiles,
+                                     (unsigned long long*)g_trace_ptr);
   return (int)e;
 }
 
@@ -307,32 +418,18 @@ int launch_decode(const MmArgs& a) {
     set_error("b2q_decode: unsupported (bits=%d M=%d K=%d N=%d group=%d)", a.bits, a.M, a.K, a.N, a.group_size);
     return -1;
   }
-  const int quads = a.K / 128, NT = a.N / 32;
-  int warps = a.tune_warps > 0 ? a.tune_warps : 4;
-  int ks;
-  if (a.tune_ks > 0) {
-    ks = a.tune_ks;
-  } else {
-    ks = 1;
-    while (ks < 8 && NT * ks < 148 * 6 && quads / (ks * 2) >= warps) ks *= 2;
-  }
-  if (ks > quads) ks = quads;
-  int qpc = (quads + ks - 1) / ks;
-  // dynamic smem budget: M * qpc * 256 B of staged activations
-  while ((size_t)a.M * qpc * 256 > 160 * 1024 && ks < 16) {
-    ks *= 2;
-    qpc = (quads + ks - 1) / ks;
-  }
-  if ((size_t)a.M * qpc * 256 > 160 * 1024) {
-    set_error("b2q_decode: K=%d too large for M=%d", a.K, a.M);
+  DecodeCfg c;
+  if (!decode_config(a, c)) {
+    set_error("b2q_decode: no configuration fits shared memory for M=%d K=%d (ks=%d warps=%d)", a.M, a.K, a.tune_ks,
+              a.tune_warps);
     return -1;
   }
   const bool asym = a.qzeros != nullptr, g64 = a.group_size == 64;
-#define B2Q_DEC_CASE(T)                                                                  \
-  (asym ? (g64 ? launch_decode_t<T, true, true>(a, ks, warps, qpc)                       \
-               : launch_decode_t<T, true, false>(a, ks, warps, qpc))                     \
-        : (g64 ? launch_decode_t<T, false, true>(a, ks, warps, qpc)                      \
-               : launch_decode_t<T, false, false>(a, ks, warps, qpc)))
+#define B2Q_DEC_CASE(T)                                                       \
+  (asym ? (g64 ? launch_decode_t<T, true, true>(a, c)                         \
+               : launch_decode_t<T, true, false>(a, c))                       \
+        : (g64 ? launch_decode_t<T, false, true>(a, c)                        \
+               : launch_decode_t<T, false, false>(a, c)))
   return a.dtype == 0 ? B2Q_DEC_CASE(__half) : B2Q_DEC_CASE(__nv_bfloat16);
 #undef B2Q_DEC_CASE
 }

@@ -32,5 +32,6 @@ int launch_decode(const MmArgs& a);   // 4-bit, M <= 8: mma.sync decode tier
 bool decode_supported(const MmArgs& a);
 int launch_gemm(const MmArgs& a);
 void set_error(const char* fmt, ...);
+extern void* g_trace_ptr;  // debug: device buffer for phase timestamps of the decode kernel (nullptr = off)
 
 }  // namespace b2q

@@ -75,6 +75,9 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
              const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
              size_t workspace_bytes, void* stream);
 
+/* Debug: device buffer (>= 148*16 uint64) receiving %globaltimer phase stamps of the decode kernel; NULL = off. */
+void b2q_debug_set_trace(void* device_buffer);
+
 /* out[m, k'] = x[m, perm[k']] for 16-bit elements. */
 int b2q_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, void* stream);
 

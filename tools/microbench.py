@@ -53,29 +53,31 @@ def time_graph(fn, iters=20):
     return e0.elapsed_time(e1) / iters * 1e3  # us per graph
 
 
-def gemv():
+def gemv(MB=1):
     p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
     for K, N in SHAPES:
         nbytes = K * N // 2
         copies = max(2, int(300e6 // nbytes) + 1)  # rotate > L2 (126 MB) of distinct weights
+        if os.environ.get("MB_L2") == "1":
+            copies = 1  # weights stay L2-resident: measures latency chain + L2 streaming
         mods = build(K, N, copies)
-        x = (torch.randn(1, K, device="cuda") * 0.5).to(torch.float16)
-        out = torch.empty(1, N, dtype=torch.float16, device="cuda")
-        alg = algorithmic_bytes(K, N, 128, 4, 1)
+        x = (torch.randn(MB, K, device="cuda") * 0.5).to(torch.float16)
+        out = torch.empty(MB, N, dtype=torch.float16, device="cuda")
+        alg = algorithmic_bytes(K, N, 128, 4, MB)
         res = []
-        for ks in (0, 1, 2, 4, 8, 16):
-            for warps in ((0,) if ks == 0 else (2, 4, 8)):
+        for ks in (0, 1, 2, 4, 8):
+            for warps in ((0,) if ks == 0 else (8, 16)):
                 quads = K // 128
-                if ks > 0 and (4 * -(-quads // ks) > 128 or ks > quads):
+                if ks > 0 and ks > quads:
                     continue
 
                 def fn():
                     st = torch.cuda.current_stream().cuda_stream
-                    for m in mods:
-                        g.check(g.lib.b2q_gemv(p(x), p(m.packed), p(m.scales.data), None, None, None, p(out), K, N,
-                                               4, 128, 0, ks, warps, st), "gemv")
+                    for m in (mods * (16 if len(mods) == 1 else 1)):
+                        g.check(g.lib.b2q_decode(p(x), p(m.packed), p(m.scales.data), None, None, None, p(out), MB, K,
+                                                 N, 4, 128, 0, ks, warps, st), "decode")
                 try:
-                    us = time_graph(fn) / copies
+                    us = time_graph(fn) / (16 if copies == 1 else copies)
                 except Exception as e:  # noqa: BLE001
                     print("fail", K, N, ks, warps, e)
                     continue
@@ -114,6 +116,6 @@ def gemm(Ms=(2048,)):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemv"
     if what == "gemv":
-        gemv()
+        gemv(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     elif what == "gemm":
         gemm(tuple(int(a) for a in sys.argv[2:]) or (2048,))
