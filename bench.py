@@ -213,9 +213,28 @@ def cpu_layer_step(mods, h):
     return mods["down_proj"].forward(g)
 
 
+def pick_cpu_threads(mods, h):
+    """The aten int4pack GEMV does not scale to every core of a big host: take the fastest of a few thread counts."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+    best = (None, 1e30)
+    for c in cands:
+        torch.set_num_threads(c)
+        cpu_layer_step(mods, h)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            cpu_layer_step(mods, h)
+        dt = (time.perf_counter() - t0) / 2
+        if dt < best[1]:
+            best = (c, dt)
+    torch.set_num_threads(best[0])
+    return best[0]
+
+
 def time_cpu_baseline(budget_s=12.0, min_iters=3):
     mods = cpu_layer()
     h = (torch.randn(1, CFG["hidden"]) * 0.5).to(torch.float16)
+    pick_cpu_threads(mods, h)
     for _ in range(2):
         cpu_layer_step(mods, h)
     n, t0 = 0, time.perf_counter()
@@ -232,9 +251,9 @@ def time_cpu_baseline(budget_s=12.0, min_iters=3):
 def reference_arm(args, rank):
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
     mods = cpu_layer()
     h = (torch.randn(1, CFG["hidden"]) * 0.5).to(torch.float16)
+    pick_cpu_threads(mods, h)
     for _ in range(max(args.warmup, 1)):
         cpu_layer_step(mods, h)
     t0 = time.perf_counter()
@@ -362,7 +381,6 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
         v, n, per_layer = time_cpu_baseline()
         cpu_base = {"value": v, "unit": "tok/s", "cores": torch.get_num_threads(), "kind": "port",
                     "sample": f"{n} passes over 1 of 32 decoder layers (7 QuantLinears, M=1) on the restated "
@@ -382,7 +400,7 @@ def main():
                 "timing": "CUDA graph of the whole step, CUDA events around K replays, max over ranks",
             },
             "roofline": {
-                "kernel": "gemv_kernel (cluster split-K FHFMA GEMV), 224 launches per step",
+                "kernel": "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL), 224 launches per step",
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
                 "algorithmic_bytes_per_launch": alg_bytes_step / n_lin, "traffic": None,

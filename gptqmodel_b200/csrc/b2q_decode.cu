@@ -366,7 +366,9 @@ static bool decode_config(const MmArgs& a, DecodeCfg& best) {
       if (smem > 200 * 1024) continue;
       const int qpw = (qpc + warps - 1) / warps;          // quads per warp per tile
       // critical path: tiles * quads-per-warp, plus a per-tile barrier and a fixed per-kernel part
-      const double cost = (double)max_tiles * (qpw + 0.35) + (ks > 1 ? 1.5 : 0.0) + (warps == 4 ? 0.3 * max_tiles * qpw : 0.0);
+      // calibrated on the B200 sweep (profiles/r01_decode_notes.md): per tile = quads/warp + barrier epilogue,
+      // split-K adds a cluster barrier + DSMEM pass, fewer warps hide less latency
+      const double cost = (double)max_tiles * (qpw + 0.35) + (ks > 1 ? 0.6 : 0.0) + (16 - warps) * 0.04 * max_tiles * qpw;
       if (cost < best_cost) {
         best_cost = cost;
         best = DecodeCfg{C, ks, warps, qpc, ks > 1 ? max_tiles : 0, smem};
