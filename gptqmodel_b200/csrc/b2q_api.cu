@@ -168,6 +168,10 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
   if (M == 0) return 0;
   MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
                        workspace_bytes, stream);
+  {
+    const char* e = getenv("B2Q_GEMM_1CTA");  // debugging / A-B measurements: keep the single-CTA tier
+    if (e != nullptr && e[0] == '1') a.tune_ks = -1;
+  }
   return check_cuda(launch_gemm(a), "b2q_gemm");
 }
 
@@ -181,6 +185,10 @@ int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t*
                        workspace_bytes, stream);
   if (decode_supported(a)) return check_cuda(launch_decode(a), "b2q_mm(decode)");
   if (M == 1 && bits == 8 && K % 128 == 0) return check_cuda(launch_gemv(a), "b2q_mm(gemv)");
+  {
+    const char* e = getenv("B2Q_GEMM_1CTA");
+    if (e != nullptr && e[0] == '1') a.tune_ks = -1;
+  }
   return check_cuda(launch_gemm(a), "b2q_mm(gemm)");
 }
 

@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include "b2q_common.cuh"
+#include "b2q_dequant.cuh"
 #include "b2q_internal.h"
 
 namespace b2q {
@@ -31,147 +32,20 @@ struct GemmCfg {
   static constexpr int A_BYTES = MT * 128 * G_BK * 2;
   static constexpr int B_BYTES = G_BN * G_BK * 2;
   static constexpr int P_CHUNK_BYTES = 4 * SUB * 512;  // 8-bit: 4 feature tiles (of 32) x 32 k
-  static constexpr int P_BYTES = 2 * P_CHUNK_BYTES;    // 128 features x 64 k (4-bit: one 4 KB T4 row block)
+  // 128 features x 64 k of packed codes (4-bit: one 4 KB T4 row block) + for 4-bit the scale / zero-point rows of
+  // the (up to 2) groups of the block: 2 x (256 B scales + 64 B packed zeros), staged by the producer
+  static constexpr int P_BYTES = 2 * P_CHUNK_BYTES + (BITS == 4 ? 1024 : 0);
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + P_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = MT * G_BN;
 };
 
-struct SZRaw {
-  uint32_t s;   // scale, 16-bit payload
-  uint32_t zw;  // packed zero word (or unused)
-};
-
-template <typename T, int BITS, bool ASYM>
-__device__ __forceinline__ SZRaw load_sz(const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, int g,
-                                         int n, int N) {
-  SZRaw r;
-  r.s = *reinterpret_cast<const uint16_t*>(scales + (size_t)g * N + n);
-  r.zw = 0;
-  if (ASYM) {
-    constexpr int PF = 32 / BITS;
-    r.zw = qzeros[(size_t)g * (N / PF) + n / PF];
-  }
-  return r;
-}
-
-// exact dequant of one packed uint4 (32 k of one feature for 4-bit, 16 k for 8-bit) into K-consecutive
-// 16-byte groups; out[i] holds 8 consecutive k.
-template <typename T, int BITS>
-struct Dequant;
-
-// 4-bit fragment-major uint4 (see b2q_common.cuh): features (g, g+8) x 16 consecutive k.
-// lo[c] / hi[c] = 8 consecutive k (chunk c = 0,1 of the lane's 16) of feature g / g+8, exactly (q - z) * s.
-template <>
-struct Dequant<__half, 4> {
-  __device__ static __forceinline__ void run(const uint4& pv, uint32_t slo16, int zlo_i, uint32_t shi16, int zhi_i,
-                                             uint4 (&lo)[2], uint4 (&hi)[2]) {
-    const uint32_t slu = slo16 | (slo16 << 16), shu = shi16 | (shi16 << 16);
-    const __half2 sl = *reinterpret_cast<const __half2*>(&slu), sh = *reinterpret_cast<const __half2*>(&shu);
-    const __half2 zlo = __float2half2_rn(1024.f + (float)zlo_i);  // exact
-    const __half2 zhi = __float2half2_rn(-(64.f + (float)zhi_i));  // exact
-    const __half2 sixteenth = __float2half2_rn(0.0625f);
-    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
-    uint32_t l[8], u[8];
-#pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-      uint32_t h[4];
-      ET<__half>::unpack_w4(w[s4], h);
-      __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[0]), zlo), sl);
-      __half2 v1 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[1]), sixteenth, zhi), sh);
-      __half2 v2 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h[2]), zlo), sl);
-      __half2 v3 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h[3]), sixteenth, zhi), sh);
-      l[2 * s4] = *reinterpret_cast<uint32_t*>(&v0);
-      l[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v2);
-      u[2 * s4] = *reinterpret_cast<uint32_t*>(&v1);
-      u[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v3);
-    }
-    lo[0] = make_uint4(l[0], l[1], l[2], l[3]);
-    lo[1] = make_uint4(l[4], l[5], l[6], l[7]);
-    hi[0] = make_uint4(u[0], u[1], u[2], u[3]);
-    hi[1] = make_uint4(u[4], u[5], u[6], u[7]);
-  }
-};
-
-template <>
-struct Dequant<__nv_bfloat16, 4> {
-  __device__ static __forceinline__ void run(const uint4& pv, uint32_t slo16, int zlo_i, uint32_t shi16, int zhi_i,
-                                             uint4 (&lo)[2], uint4 (&hi)[2]) {
-    const uint32_t slu = slo16 | (slo16 << 16), shu = shi16 | (shi16 << 16);
-    const __nv_bfloat162 sl = *reinterpret_cast<const __nv_bfloat162*>(&slu);
-    const __nv_bfloat162 sh = *reinterpret_cast<const __nv_bfloat162*>(&shu);
-    const __nv_bfloat162 zl = __float2bfloat162_rn(128.f + (float)zlo_i);  // exact (<= 143)
-    const __nv_bfloat162 zh = __float2bfloat162_rn(128.f + (float)zhi_i);
-    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
-    uint32_t l[8], u[8];
-#pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-      uint32_t h[4];
-      ET<__nv_bfloat16>::unpack_w4(w[s4], h);
-      __nv_bfloat162 v0 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[0]), zl), sl);
-      __nv_bfloat162 v1 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[1]), zh), sh);
-      __nv_bfloat162 v2 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[2]), zl), sl);
-      __nv_bfloat162 v3 = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&h[3]), zh), sh);
-      l[2 * s4] = *reinterpret_cast<uint32_t*>(&v0);
-      l[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v2);
-      u[2 * s4] = *reinterpret_cast<uint32_t*>(&v1);
-      u[2 * s4 + 1] = *reinterpret_cast<uint32_t*>(&v3);
-    }
-    lo[0] = make_uint4(l[0], l[1], l[2], l[3]);
-    lo[1] = make_uint4(l[4], l[5], l[6], l[7]);
-    hi[0] = make_uint4(u[0], u[1], u[2], u[3]);
-    hi[1] = make_uint4(u[4], u[5], u[6], u[7]);
-  }
-};
-
-template <>
-struct Dequant<__half, 8> {
-  // 16 k per uint4 -> 2 x uint4
-  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[2]) {
-    const uint32_t s2u = s16 | (s16 << 16);
-    const __half2 s2 = *reinterpret_cast<const __half2*>(&s2u);
-    const __half2 zb = __float2half2_rn(1024.f + (float)z);  // exact (<= 1279)
-    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
-    uint32_t r[8];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      uint32_t p0 = __byte_perm(w[t], 0x64006400u, 0x7150);
-      uint32_t p1 = __byte_perm(w[t], 0x64006400u, 0x7352);
-      __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&p0), zb), s2);
-      __half2 v1 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&p1), zb), s2);
-      r[2 * t] = *reinterpret_cast<uint32_t*>(&v0);
-      r[2 * t + 1] = *reinterpret_cast<uint32_t*>(&v1);
-    }
-    o[0] = make_uint4(r[0], r[1], r[2], r[3]);
-    o[1] = make_uint4(r[4], r[5], r[6], r[7]);
-  }
-};
-
-template <>
-struct Dequant<__nv_bfloat16, 8> {
-  __device__ static __forceinline__ void run(const uint4& pv, uint32_t s16, int z, uint4 (&o)[2]) {
-    const float s = __uint_as_float(s16 << 16);
-    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
-    uint32_t r[8];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      // (q - z) exact in fp32, product with the bf16 scale exact in fp32, ONE rounding to bf16
-      const float q0 = (float)((int)(w[t] & 0xFFu) - z), q1 = (float)((int)((w[t] >> 8) & 0xFFu) - z);
-      const float q2 = (float)((int)((w[t] >> 16) & 0xFFu) - z), q3 = (float)((int)(w[t] >> 24) - z);
-      r[2 * t] = ET<__nv_bfloat16>::pack2(q0 * s, q1 * s);
-      r[2 * t + 1] = ET<__nv_bfloat16>::pack2(q2 * s, q3 * s);
-    }
-    o[0] = make_uint4(r[0], r[1], r[2], r[3]);
-    o[1] = make_uint4(r[4], r[5], r[6], r[7]);
-  }
-};
-
 template <typename T, int BITS, bool ASYM, int MT, int STAGES>
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
                 const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, const T* __restrict__ bias,
-                T* __restrict__ out, int M, int K, int N, int group_size) {
+                T* __restrict__ out, int M, int K, int N, int group_size, int gshc) {
   using C = GemmCfg<BITS, MT, STAGES>;
   using E = ET<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -223,13 +97,25 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_full + 8 * s, C::A_BYTES + (BITS == 4 ? pbytes4 : 2 * pbytes8));
+        // 4-bit: scale / zero rows of the block's group(s) travel with the packed codes (no LDG in the dequant warps)
+        const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
+        const int nrows = (g1 != g0) ? 2 : 1;
+        const uint32_t sbytes = (uint32_t)min(128, N - n0) * 2u, zbytes = ASYM ? sbytes / 4u : 0u;
+        mbar_expect_tx(bar_full + 8 * s,
+                       C::A_BYTES + (BITS == 4 ? pbytes4 + nrows * (sbytes + zbytes) : 2 * pbytes8));
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
           tma_load_2d(sA + s * C::A_BYTES + mt * (128 * G_BK * 2), &tmap_x, bar_full + 8 * s, kb * G_BK,
                       m0 + mt * 128);
         if (BITS == 4) {
           bulk_load(sP + s * C::P_BYTES, packed + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_full + 8 * s);
+          for (int r = 0; r < nrows; ++r) {
+            const int gr = r ? g1 : g0;
+            bulk_load(sP + s * C::P_BYTES + 4096 + r * 320, scales + (size_t)gr * N + n0, sbytes, bar_full + 8 * s);
+            if (ASYM)
+              bulk_load(sP + s * C::P_BYTES + 4096 + r * 320 + 256, qzeros + (size_t)gr * (N >> 3) + (n0 >> 3),
+                        zbytes, bar_full + 8 * s);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
@@ -267,7 +153,6 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     const int t = threadIdx.x - 64;  // 0..127
     constexpr int PF = 32 / BITS;
     constexpr int ZSYM = 1 << (BITS - 1);
-    const int gchunks = group_size >> 5;  // 32-k chunks per group
     if (BITS == 4) {
       // thread owns two fragment-major uint4 per stage: feature tiles (t>>5) and (t>>5)+4, lane' = t&31 = 4g+tt
       const int lp = t & 31, g = lp >> 2, tt = lp & 3;
@@ -276,33 +161,29 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       f[1] = f[0] + 8;
       f[2] = f[0] + 64;
       f[3] = f[0] + 72;
-      int nf[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) nf[i] = (n0 + f[i] < N) ? n0 + f[i] : 0;
-      // this lane's 16 k of block kb lie in 32-k chunk 2*kb + (tt>>1)
-      SZRaw cur[4], nxt[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = load_sz<T, BITS, ASYM>(scales, qzeros, (tt >> 1) / gchunks, nf[i], N);
+      // this lane's 16 k of block kb lie in 32-k chunk 2*kb + (tt>>1); its scale / zero row was staged by the producer
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        if (kb + 1 < nkb) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            nxt[i] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2 + (tt >> 1)) / gchunks, nf[i], N);
-        }
         mbar_wait(bar_full + 8 * s, ph);
-        const uint4* pj = reinterpret_cast<const uint4*>(smem + (sP - smem_base) + s * C::P_BYTES);
+        const uint8_t* pst = smem + (sP - smem_base) + s * C::P_BYTES;
+        const uint4* pj = reinterpret_cast<const uint4*>(pst);
+        const int grow = ((2 * kb + (tt >> 1)) >> gshc) - ((2 * kb) >> gshc);  // 0 or 1
+        const uint8_t* srow = pst + 4096 + grow * 320;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const uint4 pv = pj[t + u * 128];
+          const uint32_t s_lo = *reinterpret_cast<const uint16_t*>(srow + f[2 * u] * 2);
+          const uint32_t s_hi = *reinterpret_cast<const uint16_t*>(srow + f[2 * u + 1] * 2);
           int zl = ZSYM, zh = ZSYM;
           if (ASYM) {
-            zl = (int)((cur[2 * u].zw >> (4 * g)) & 15u);      // (n0 + f) % 8 == g for both rows
-            zh = (int)((cur[2 * u + 1].zw >> (4 * g)) & 15u);
+            const uint32_t zwl = *reinterpret_cast<const uint32_t*>(srow + 256 + (f[2 * u] >> 3) * 4);
+            const uint32_t zwh = *reinterpret_cast<const uint32_t*>(srow + 256 + (f[2 * u + 1] >> 3) * 4);
+            zl = (int)((zwl >> (4 * g)) & 15u);  // feature % 8 == g for both rows
+            zh = (int)((zwh >> (4 * g)) & 15u);
           }
           uint4 lo[2], hi[2];
-          Dequant<T, 4>::run(pv, cur[2 * u].s, zl, cur[2 * u + 1].s, zh, lo, hi);
+          Dequant<T, 4>::run(pv, s_lo, zl, s_hi, zh, lo, hi);
           const uint32_t sw = (uint32_t)g;  // (row & 7) for rows f and f+8
           const uint32_t rlo = sB + s * C::B_BYTES + f[2 * u] * 128;
           const uint32_t rhi = rlo + 8 * 128;
@@ -319,8 +200,6 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_bready + 8 * s);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
       }
     } else {
       const int n = n0 + t;
@@ -328,13 +207,13 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       const int ntl = t >> 5;
       SZRaw cur[2], nxt[2];
       cur[0] = load_sz<T, BITS, ASYM>(scales, qzeros, 0, nsafe, N);
-      cur[1] = load_sz<T, BITS, ASYM>(scales, qzeros, 1 / gchunks, nsafe, N);
+      cur[1] = load_sz<T, BITS, ASYM>(scales, qzeros, 1 >> gshc, nsafe, N);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         if (kb + 1 < nkb) {
-          nxt[0] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2) / gchunks, nsafe, N);
-          nxt[1] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 3) / gchunks, nsafe, N);
+          nxt[0] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2) >> gshc, nsafe, N);
+          nxt[1] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 3) >> gshc, nsafe, N);
         }
         mbar_wait(bar_full + 8 * s, ph);
         const uint32_t brow = sB + s * C::B_BYTES + t * 128;
@@ -448,6 +327,14 @@ static int make_x_tmap(CUtensorMap* map, const void* x, int M, int K, int dtype)
   return 0;
 }
 
+// log2(32-k chunks per group); 31 for per-channel (every chunk maps to group 0)
+int gemm_gshc(const MmArgs& a) {
+  if (a.group_size == 32) return 0;
+  if (a.group_size == 64) return 1;
+  if (a.group_size == 128) return 2;
+  return 31;
+}
+
 template <typename T, int BITS, bool ASYM, int MT, int STAGES>
 static int launch_gemm_t(const MmArgs& a, const void* x) {
   using C = GemmCfg<BITS, MT, STAGES>;
@@ -466,7 +353,7 @@ static int launch_gemm_t(const MmArgs& a, const void* x) {
   dim3 grid((a.N + G_BN - 1) / G_BN, (a.M + 128 * MT - 1) / (128 * MT), 1);
   kern<<<grid, G_THREADS, C::SMEM_BYTES, a.stream>>>(tmap, (const uint4*)a.packed, (const T*)a.scales,
                                                      (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M,
-                                                     a.K, a.N, a.group_size);
+                                                     a.K, a.N, a.group_size, gemm_gshc(a));
   return (int)cudaGetLastError();
 }
 
@@ -486,6 +373,7 @@ int launch_gemm(const MmArgs& a) {
     if (e != 0) return e;
     x = a.workspace;
   }
+  if (a.bits == 4 && a.M > 128 && a.tune_ks != -1) return launch_gemm2(a, x);  // CTA-pair tier (tune_ks -1: force 1-CTA)
   const bool asym = a.qzeros != nullptr;
   const bool big = a.M > 128;
 #define B2Q_GEMM_CASE(T, BITS, ST)                                                              \

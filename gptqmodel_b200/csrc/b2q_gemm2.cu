@@ -1,0 +1,323 @@
+// b2q_gemm2.cu — prefill tier on CTA PAIRS: out[M, N] = x[M, K] @ dequant(W4)[K, N] with tcgen05.mma.cta_group::2.
+//
+// Why pairs: the 1-CTA tier (b2q_gemm.cu) is bound by SHARED-MEMORY BANDWIDTH, not by the tensor pipe — per 64-k block
+// a 256x128 CTA tile moves 64 KB of UMMA operand reads + 16 KB of dequant stores + 36 KB of TMA writes through the
+// 128 B/clk shared memory in the 512 clk the MMAs need (234 B/clk wanted -> ~55 % of peak, which is what was
+// measured: profiles/r01_gemm_notes.md).  With cta_group::2 a pair of SMs computes a 256 (tokens) x 256 (features)
+// tile; each CTA stages only ITS 128 token rows of A and dequantises only ITS 128 feature rows of B, the tensor cores
+// of both SMs read both halves: 32 KB operand reads + 16 KB dequant stores + 20 KB TMA per 512 clk per SM (~144 B/clk).
+//
+//   cluster (2,1,1); rank r = %cluster_ctarank owns tokens m0+128r.. and features n0+128r..
+//   warp 0      producer : TMA (cp.async.bulk.tensor .cta_group::2) of its A half, signalling the LEADER's mbarrier;
+//                          cp.async.bulk of its 4 KB packed-weight block on a local mbarrier
+//   warp 1      MMA      : both CTAs allocate TMEM (cta_group::2); the leader's elected lane issues
+//                          tcgen05.mma.cta_group::2.kind::f16 (M=256, N=256, K=16), tcgen05.commit multicast to both
+//   warps 2..5  dequant  : as in the 1-CTA tier; completion arrives on the leader's mbarrier (remote arrive);
+//                          afterwards epilogue of the CTA's own 128 x 256 accumulator (TMEM -> regs -> global)
+#include <cuda.h>
+
+#include "b2q_common.cuh"
+#include "b2q_dequant.cuh"
+#include "b2q_internal.h"
+
+namespace b2q {
+
+constexpr int G2_BK = 64;
+constexpr int G2_THREADS = 192;
+constexpr int G2_STAGES = 5;
+constexpr int G2_A_BYTES = 128 * G2_BK * 2;   // 16 KB: this CTA's 128 token rows
+constexpr int G2_B_BYTES = 128 * G2_BK * 2;   // 16 KB: this CTA's 128 feature rows (dequantised)
+constexpr int G2_P_BYTES = 4096 + 1024;       // packed int4 block of the same 128 features x 64 k + scale/zero rows
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES + G2_P_BYTES;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 512 + 1024;
+constexpr int G2_TMEM_COLS = 256;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics on purpose: the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR per arrive and was 43 %
+  // of all stall samples (profiles/r01_gemm2_r1a.txt); ordering of the dequantised tile towards the tensor cores is
+  // given by fence.proxy.async + the CTA-wide named barrier that precedes this single arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0;\n"
+      "  tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
+template <typename T, bool ASYM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+    gemm2_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
+                 const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, const T* __restrict__ bias,
+                 T* __restrict__ out, int M, int K, int N, int group_size, int gshc) {
+  using E = ET<T>;
+  constexpr int STAGES = G2_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + STAGES * G2_A_BYTES;
+  const uint32_t sP = sB + STAGES * G2_B_BYTES;
+  const uint32_t sBar = sP + STAGES * G2_P_BYTES;
+  // leader-owned (used through cluster addresses by the peer): fullA, bready.  per-CTA: fullP, empty, tfull
+  const uint32_t bar_fullA = sBar, bar_bready = sBar + 8 * STAGES, bar_fullP = sBar + 16 * STAGES;
+  const uint32_t bar_empty = sBar + 24 * STAGES, bar_tfull = sBar + 32 * STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 32 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int FT = N >> 4;
+  const int n0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;  // this CTA's 128 feature rows
+  const int npair0 = (blockIdx.x >> 1) * 256;               // the pair's 256 output columns
+  const int m0 = blockIdx.y * 256 + (int)rank * 128;         // this CTA's 128 token rows
+  const int ft0 = n0 >> 4;
+  const int nkb = K / G2_BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_fullA + 8 * s, 1);     // leader: its own arrive.expect_tx (both CTAs' TMA bytes)
+      mbar_init(bar_bready + 8 * s, 2);    // leader: ONE aggregated arrive per CTA (remote arrives are slow)
+      mbar_init(bar_fullP + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(G2_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      const int nft = max(0, min(8, FT - ft0));
+      const uint32_t pbytes = (uint32_t)nft * 512u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (rank == 0) mbar_expect_tx(bar_fullA + 8 * s, 2 * G2_A_BYTES);
+        tma_load_2d_cg2(sA + s * G2_A_BYTES, &tmap_x, mapa_u32(bar_fullA + 8 * s, 0), kb * G2_BK, m0);
+        if (pbytes > 0) {
+          const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
+          const int nrows = (g1 != g0) ? 2 : 1;
+          const uint32_t sbytes = (uint32_t)min(128, N - n0) * 2u, zbytes = ASYM ? sbytes / 4u : 0u;
+          mbar_expect_tx(bar_fullP + 8 * s, pbytes + nrows * (sbytes + zbytes));
+          bulk_load(sP + s * G2_P_BYTES, packed + ((size_t)kb * FT + ft0) * 32, pbytes, bar_fullP + 8 * s);
+          for (int r = 0; r < nrows; ++r) {
+            const int gr = r ? g1 : g0;
+            bulk_load(sP + s * G2_P_BYTES + 4096 + r * 320, scales + (size_t)gr * N + n0, sbytes, bar_fullP + 8 * s);
+            if (ASYM)
+              bulk_load(sP + s * G2_P_BYTES + 4096 + r * 320 + 256, qzeros + (size_t)gr * (N >> 3) + (n0 >> 3),
+                        zbytes, bar_fullP + 8 * s);
+          }
+        } else {
+          mbar_arrive(bar_fullP + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(E::FMT, 256, 256);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_fullA + 8 * s, ph);
+        mbar_wait(bar_bready + 8 * s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = umma_desc_k_sw128(sA + s * G2_A_BYTES);
+          const uint64_t bdesc = umma_desc_k_sw128(sB + s * G2_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k)
+            umma_f16_cg2(tbase, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_cg2_mc(bar_empty + 8 * s, 3);
+          if (kb == nkb - 1) umma_commit_cg2_mc(bar_tfull, 3);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ dequant warps ================================
+    const int t = threadIdx.x - 64;  // 0..127
+    constexpr int ZSYM = 8;
+    const int lp = t & 31, g = lp >> 2, tt = lp & 3;
+    int f[4];
+    f[0] = (t >> 5) * 16 + g;
+    f[1] = f[0] + 8;
+    f[2] = f[0] + 64;
+    f[3] = f[0] + 72;
+    const uint32_t bready_leader = mapa_u32(bar_bready, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(bar_fullP + 8 * s, ph);
+      const uint8_t* pst = smem + (sP - smem_base) + s * G2_P_BYTES;
+      const uint4* pj = reinterpret_cast<const uint4*>(pst);
+      const int grow = ((2 * kb + (tt >> 1)) >> gshc) - ((2 * kb) >> gshc);  // 0 or 1
+      const uint8_t* srow = pst + 4096 + grow * 320;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint4 pv = pj[t + u * 128];
+        const uint32_t s_lo = *reinterpret_cast<const uint16_t*>(srow + f[2 * u] * 2);
+        const uint32_t s_hi = *reinterpret_cast<const uint16_t*>(srow + f[2 * u + 1] * 2);
+        int zl = ZSYM, zh = ZSYM;
+        if (ASYM) {
+          const uint32_t zwl = *reinterpret_cast<const uint32_t*>(srow + 256 + (f[2 * u] >> 3) * 4);
+          const uint32_t zwh = *reinterpret_cast<const uint32_t*>(srow + 256 + (f[2 * u + 1] >> 3) * 4);
+          zl = (int)((zwl >> (4 * g)) & 15u);
+          zh = (int)((zwh >> (4 * g)) & 15u);
+        }
+        uint4 lo[2], hi[2];
+        Dequant<T, 4>::run(pv, s_lo, zl, s_hi, zh, lo, hi);
+        const uint32_t sw = (uint32_t)g;
+        const uint32_t rlo = sB + s * G2_B_BYTES + f[2 * u] * 128;
+        const uint32_t rhi = rlo + 8 * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t off = (((uint32_t)(2 * tt + c)) ^ sw) << 4;
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rlo + off), "r"(lo[c].x), "r"(lo[c].y),
+                       "r"(lo[c].z), "r"(lo[c].w)
+                       : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rhi + off), "r"(hi[c].x), "r"(hi[c].y),
+                       "r"(hi[c].z), "r"(hi[c].w)
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      // aggregate the 128 dequant threads on a named barrier, then ONE (possibly remote) arrive per CTA: 128
+      // individual remote mbarrier arrives per stage serialised on the cluster network and cost more than the MMAs
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t == 0) mbar_arrive_cluster(bready_leader + 8 * s);
+    }
+
+    // ================================ epilogue: own 128 tokens x 256 features ================================
+    mbar_wait(bar_tfull, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int cc = 0; cc < 8; ++cc) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tbase + ((uint32_t)(q * 32) << 16) + cc * 32, r);
+      tmem_ld_wait();
+      const int nc = npair0 + cc * 32;
+      if (row < M && nc < N) {
+        T* dst = out + (size_t)row * N + nc;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float f0 = __uint_as_float(r[v * 8 + 2 * i]), f1 = __uint_as_float(r[v * 8 + 2 * i + 1]);
+            if (bias != nullptr) {
+              f0 = E::to_f(E::from_f(f0)) + E::to_f(bias[nc + v * 8 + 2 * i]);
+              f1 = E::to_f(E::from_f(f1)) + E::to_f(bias[nc + v * 8 + 2 * i + 1]);
+            }
+            pk[i] = E::pack2(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();  // both CTAs done with TMEM / each other's shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(G2_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_x_tmap2(CUtensorMap* map, const void* x, int M, int K, int dtype) {
+  static EncodeTiledFn2 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn2>(p);
+  }
+  if (fn == nullptr) {
+    set_error("b2q_gemm2: cuTensorMapEncodeTiled not available from the driver");
+    return -1;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)G2_BK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("b2q_gemm2: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -1;
+  }
+  return 0;
+}
+
+template <typename T, bool ASYM>
+static int launch_gemm2_t(const MmArgs& a, const void* x) {
+  CUtensorMap tmap;
+  if (make_x_tmap2(&tmap, x, a.M, a.K, a.dtype) != 0) return -1;
+  auto kern = gemm2_kernel<T, ASYM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("b2q_gemm2: cannot opt in to %d bytes of shared memory: %s", G2_SMEM_BYTES, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  dim3 grid(2 * ((a.N + 255) / 256), (a.M + 255) / 256, 1);
+  kern<<<grid, G2_THREADS, G2_SMEM_BYTES, a.stream>>>(tmap, (const uint4*)a.packed, (const T*)a.scales,
+                                                      (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M,
+                                                      a.K, a.N, a.group_size, gemm_gshc(a));
+  return (int)cudaGetLastError();
+}
+
+// x must already be the (act-order permuted, if any) activation matrix
+int launch_gemm2(const MmArgs& a, const void* x) {
+  const bool asym = a.qzeros != nullptr;
+  if (a.dtype == 0) return asym ? launch_gemm2_t<__half, true>(a, x) : launch_gemm2_t<__half, false>(a, x);
+  return asym ? launch_gemm2_t<__nv_bfloat16, true>(a, x) : launch_gemm2_t<__nv_bfloat16, false>(a, x);
+}
+
+}  // namespace b2q

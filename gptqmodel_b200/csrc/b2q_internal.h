@@ -31,6 +31,8 @@ int launch_gemv(const MmArgs& a);     // 8-bit, M == 1: CUDA-core FHFMA GEMV
 int launch_decode(const MmArgs& a);   // 4-bit, M <= 8: mma.sync decode tier
 bool decode_supported(const MmArgs& a);
 int launch_gemm(const MmArgs& a);
+int launch_gemm2(const MmArgs& a, const void* x);
+int gemm_gshc(const MmArgs& a);  // 4-bit, CTA-pair (cta_group::2) tier; x already permuted
 void set_error(const char* fmt, ...);
 extern void* g_trace_ptr;  // debug: device buffer for phase timestamps of the decode kernel (nullptr = off)
 
