@@ -429,8 +429,13 @@ def main():
             line["invalid"] = f"debug run with {args.layers} layers"
         print(json.dumps(line))
     if world > 1:
+        # Tearing an NCCL process group down while captured CUDA graphs still hold its kernels hangs in
+        # destroy_process_group (seen on the 2-GPU box): drop the graphs, sync, and leave without the destroy.
+        del g_dec, g_pre
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
