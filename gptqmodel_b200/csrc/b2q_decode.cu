@@ -78,6 +78,17 @@ __device__ __forceinline__ void load_dscale(DScale<ASYM, G64>& q, const T* __res
   }
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
+  return r;
+}
+
 __device__ __forceinline__ void issue_quad(uint32_t dst, uint32_t bar, const uint4* __restrict__ src,
                                            size_t kb_stride) {
   mbar_expect_tx(bar, DEC_QUAD_BYTES);
@@ -88,6 +99,12 @@ __device__ __forceinline__ void issue_quad(uint32_t dst, uint32_t bar, const uin
 // Persistent-style CTA: blockIdx.x strides over the 32-feature tiles (tile = blockIdx.x + i * gridDim.x), blockIdx.y is
 // the split-K rank inside the cluster.  x is staged ONCE per CTA; the warps split the k-quads of every tile; each
 // warp's bulk-copy ring runs ahead across tile boundaries.
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+
 template <typename T, bool ASYM, bool G64>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     decode_kernel(const uint4* __restrict__ packed, const T* __restrict__ scales, const uint32_t* __restrict__ qzeros,
@@ -121,24 +138,37 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   float* red = xsum + qpc * 2 * 8;
   float* part = red + 2 * nwarps * 256;
   const uint32_t bars = smem_u32(part + max_tiles * 256) + warp * DEC_STAGES * 8;
+  int* fin = reinterpret_cast<int*>(part + max_tiles * 256) + nwarps * DEC_STAGES * 2;  // fin[2] after the mbarriers
+  if (threadIdx.x == 0) fin[0] = fin[1] = 0;
   const bool PERM = perm != nullptr;
   const size_t kb_stride = (size_t)FT * 32;
 
   // ---- 1. the first DEC_STAGES quads of this warp requested before anything else -----------------
   const int nq = (q0 + warp < q1) ? (q1 - q0 - warp + nwarps - 1) / nwarps : 0;  // quads per tile for this warp
   const int U = ntiles * nq;                                                     // units of this warp
-  auto unit_src = [&](int u) {
-    const int ti = u / nq, qi = u - ti * nq;
-    const int nt = blockIdx.x + ti * C, q = q0 + warp + qi * nwarps;
-    return packed + ((size_t)(2 * q) * FT + 2 * nt) * 32;
-  };
+  // running source pointer of the next unit to issue (lane 0): quads of a tile are 2*nwarps k-blocks apart, tiles C*64 uint4
+  const uint4* iss_tile = packed + ((size_t)(2 * (q0 + warp)) * FT + 2 * blockIdx.x) * 32;
+  const uint4* iss_src = iss_tile;
+  const size_t quad_step = (size_t)(2 * nwarps) * kb_stride;
+  int iss_q = 0, iss_u = 0;
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < DEC_STAGES; ++i) mbar_init(bars + 8 * i, 1);
     fence_mbar_init();
 #pragma unroll
-    for (int i = 0; i < DEC_STAGES; ++i)
-      if (i < U) issue_quad(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i, unit_src(i), kb_stride);
+    for (int i = 0; i < DEC_STAGES; ++i) {
+      if (iss_u < U) {
+        issue_quad(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i, iss_src, kb_stride);
+        ++iss_u;
+        if (++iss_q == nq) {
+          iss_q = 0;
+          iss_tile += (size_t)C * 64;
+          iss_src = iss_tile;
+        } else {
+          iss_src += quad_step;
+        }
+      }
+    }
   }
   DScale<ASYM, G64> cur;
   if (U > 0) load_dscale<T, ASYM, G64>(cur, scales, qzeros, q0 + warp, gsh, N, blockIdx.x * 32 + g);
@@ -192,8 +222,50 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   stamp(3);
 
   // ---- 3. loop over this CTA's tiles; inside a tile the warps split the k-quads --------------------
+  // All loop-carried addresses are 32-bit shared-window addresses / running global pointers computed ONCE here:
+  // the first version recomputed them per quad (~80 of 220 SASS instructions, profiles/r01_decode_r1c.txt).
   constexpr float ZSYM = 8.f;
   const uint32_t nrank = cluster_nctarank();
+  const uint32_t ring_a = smem_u32(ring) + lane * 16;
+  const uint32_t xf_a0 = smem_u32(sx) + (uint32_t)((g * kspan + t * 16 + warp * 128) * 2);
+  const uint32_t xs_a0 = smem_u32(xsum) + (uint32_t)((2 * t + warp * 16) * 4);
+  const uint32_t xf_qstep = (uint32_t)nwarps * 256u, xs_qstep = (uint32_t)nwarps * 64u;
+  const int gstep = (2 * nwarps) >> gsh;                    // groups between consecutive quads of this warp
+  const int g_first = (2 * (q0 + warp)) >> gsh;             // group of this warp's first quad in every tile
+  const T* sc_tile = scales + (size_t)g_first * N + blockIdx.x * 32 + g;
+  const uint32_t* zq_tile = ASYM ? qzeros + (size_t)g_first * (N >> 3) + blockIdx.x * 4 : nullptr;
+  const T* sc_next = sc_tile;   // scale pointer of the NEXT unit to prefetch
+  const uint32_t* zq_next = zq_tile;
+  int pre_q = 0;                // quad-in-tile of the next unit to prefetch
+  auto advance_prefetch = [&]() {
+    if (++pre_q == nq) {
+      pre_q = 0;
+      sc_tile += (size_t)C * 32;
+      sc_next = sc_tile;
+      if (ASYM) {
+        zq_tile += (size_t)C * 4;
+        zq_next = zq_tile;
+      }
+    } else {
+      sc_next += (size_t)gstep * N;
+      if (ASYM) zq_next += (size_t)gstep * (N >> 3);
+    }
+  };
+  auto fetch_scales = [&](DScale<ASYM, G64>& d) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      d.s[0][i] = *reinterpret_cast<const uint16_t*>(sc_next + i * 8);
+      if (ASYM) d.zw[0][i] = zq_next[i];
+    }
+    if (G64) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        d.s[G64 ? 1 : 0][i] = *reinterpret_cast<const uint16_t*>(sc_next + (size_t)N + i * 8);
+        if (ASYM) d.zw[G64 ? 1 : 0][i] = zq_next[(N >> 3) + i];
+      }
+    }
+  };
+  advance_prefetch();  // unit 0 was fetched in the prologue (cur)
   int u = 0;
   for (int ti = 0; ti < ntiles; ++ti) {
     const int nt = blockIdx.x + ti * C;
@@ -203,17 +275,16 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
 #pragma unroll
       for (int b = 0; b < 4; ++b) tot[a][b] = 0.f;
 
-    for (int qi = 0; qi < nq; ++qi, ++u) {
-      const int ql = warp + qi * nwarps;  // quad index relative to q0
+    uint32_t xf_a = xf_a0, xs_a = xs_a0;
+    for (int qi = 0; qi < nq; ++qi, ++u, xf_a += xf_qstep, xs_a += xs_qstep) {
       DScale<ASYM, G64> nxt;
       if (u + 1 < U) {
-        const int last = (qi + 1 == nq);
-        load_dscale<T, ASYM, G64>(nxt, scales, qzeros, last ? q0 + warp : q0 + ql + nwarps, gsh, N,
-                                  (last ? nt + C : nt) * 32 + g);
+        fetch_scales(nxt);
+        advance_prefetch();
       }
-      const int st = u % DEC_STAGES;
-      mbar_wait(bars + 8 * st, (uint32_t)(u / DEC_STAGES) & 1u);
-      const uint4* wq = reinterpret_cast<const uint4*>(ring + st * DEC_QUAD_BYTES) + lane;
+      const int st = u & (DEC_STAGES - 1);
+      mbar_wait(bars + 8 * st, (uint32_t)(u >> 2) & 1u);
+      const uint32_t wq_a = ring_a + st * DEC_QUAD_BYTES;
       float dd[2][2][4];  // [kbl][ftl][c]: four independent mma accumulator chains
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -227,8 +298,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         // activation fragment: token (column) g, k = 64*kb + 16t .. +15  -> 8 registers, 2 per k-step
         uint32_t bx[8];
         if (g < M) {
-          const uint4* xp = reinterpret_cast<const uint4*>(sx + (size_t)g * kspan + (ql * 2 + kbl) * 64 + t * 16);
-          const uint4 x0 = xp[0], x1 = xp[1];
+          const uint4 x0 = lds128(xf_a + kbl * 128), x1 = lds128(xf_a + kbl * 128 + 16);
           bx[0] = x0.x; bx[1] = x0.y; bx[2] = x0.z; bx[3] = x0.w;
           bx[4] = x1.x; bx[5] = x1.y; bx[6] = x1.z; bx[7] = x1.w;
         } else {
@@ -237,7 +307,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         }
 #pragma unroll
         for (int ftl = 0; ftl < 2; ++ftl) {
-          const uint4 wv = wq[(kbl * 2 + ftl) * 32];
+          const uint4 wv = lds128(wq_a + (kbl * 2 + ftl) * 512);
           const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
@@ -246,7 +316,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
             mma_16816<T>(dd[kbl][ftl], a, bx[2 * s], bx[2 * s + 1]);
           }
         }
-        const float2 xs = *reinterpret_cast<const float2*>(xsum + (ql * 2 + kbl) * 8 + 2 * t);
+        const float2 xs = lds_f2(xs_a + kbl * 32);
         xs0 += xs.x;
         xs1 += xs.y;
         if (kbl == 1 || G64) {
@@ -274,14 +344,25 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
           xs0 = xs1 = 0.f;
         }
       }
-      // recycle the stage for unit u + DEC_STAGES (all lanes have finished reading it)
+      // recycle the stage for the next not-yet-issued unit (all lanes have finished reading it)
       __syncwarp();
-      if (lane == 0 && u + DEC_STAGES < U)
-        issue_quad(smem_u32(ring) + st * DEC_QUAD_BYTES, bars + 8 * st, unit_src(u + DEC_STAGES), kb_stride);
+      if (lane == 0 && iss_u < U) {
+        issue_quad(ring_a + st * DEC_QUAD_BYTES, bars + 8 * st, iss_src, kb_stride);
+        ++iss_u;
+        if (++iss_q == nq) {
+          iss_q = 0;
+          iss_tile += (size_t)C * 64;  // next tile: 2 feature tiles x 32 uint4 per CTA stride
+          iss_src = iss_tile;
+        } else {
+          iss_src += quad_step;
+        }
+      }
       if (u + 1 < U) cur = nxt;
     }
 
     // ---- tile epilogue: warps -> CTA through (double-buffered) smem, one barrier per tile ---------
+    // (two decoupled variants were measured and were slower: "last warp to arrive reduces" and "rotating reducer
+    //  warp on a split arrive/sync named barrier" — profiles/r01_decode_notes.md)
     // tot[ftl][c]: feature nt*32 + ftl*16 + g (+8 if c >= 2), token 2t + (c & 1)
     if (ti < 5) stamp(4 + 2 * ti);
     float* rbuf = red + (ti & 1) * nwarps * 256;
@@ -313,6 +394,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
 
   // ---- 4. split-K: the cluster ranks share the tiles of the final DSMEM reduction -----------------
   if (nrank > 1) {
+    __syncthreads();  // every tile's reducer has written its partials
     cluster_sync_all();
     const uint32_t rank = cluster_ctarank();
     for (int ti = (int)rank; ti < ntiles; ti += (int)nrank) {
@@ -343,7 +425,7 @@ struct DecodeCfg {
 
 static size_t decode_smem(int M, int warps, int qpc, int max_tiles) {
   return (size_t)warps * DEC_STAGES * DEC_QUAD_BYTES + (size_t)M * qpc * 128 * 2 + (size_t)qpc * 2 * 8 * 4 +
-         (size_t)2 * warps * 256 * 4 + (size_t)max_tiles * 256 * 4 + (size_t)warps * DEC_STAGES * 8;
+         (size_t)2 * warps * 256 * 4 + (size_t)max_tiles * 256 * 4 + (size_t)warps * DEC_STAGES * 8 + 16;
 }
 
 // Pick (C tiles-columns, ks split-K ranks, warps) minimising the critical path in "quads per warp" on ~148 CTAs.
