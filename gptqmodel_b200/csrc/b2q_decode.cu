@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         advance_prefetch();
       }
       const int st = u & (DEC_STAGES - 1);
-      mbar_wait(bars + 8 * st, (uint32_t)(u >> 2) & 1u);
+      mbar_wait(bars + 8 * st, (uint32_t)(u / DEC_STAGES) & 1u);
       const uint32_t wq_a = ring_a + st * DEC_QUAD_BYTES;
       float dd[2][2][4];  // [kbl][ftl][c]: four independent mma accumulator chains
 #pragma unroll
