@@ -116,8 +116,8 @@ def synth_layer(K, N, seed, device, bits=4, gs=128):
     return dict(qweight=qw, qzeros=qz, scales=sc, g_idx=gi, bias=None, bits=bits, group_size=gs)
 
 
-def build_stack(device, rank, world, layers):
-    from gptqmodel_b200 import B200QuantLinear, tp
+def build_stack(device, rank, world, layers, fuse=True):
+    from gptqmodel_b200 import B200QuantLinear, fuse_siblings, tp
 
     stack = []
     for li in range(layers):
@@ -131,6 +131,10 @@ def build_stack(device, rank, world, layers):
                                                         CFG["group_size"], device=device)
             mods[name] = m
             del L
+        if fuse:
+            # q/k/v and gate/up consume the same activations: one decode launch each (b2q_decode_multi)
+            fuse_siblings([mods["q_proj"], mods["k_proj"], mods["v_proj"]])
+            fuse_siblings([mods["gate_proj"], mods["up_proj"]])
         stack.append(mods)
     torch.cuda.empty_cache()
     return stack
@@ -288,6 +292,7 @@ def main():
     ap.add_argument("--prefill-iters", type=int, default=0, help="0 = auto")
     ap.add_argument("--layers", type=int, default=CFG["layers"], help="debug: fewer layers (result marked invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinear (224/step) instead of fusing q/k/v and gate/up")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -312,7 +317,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     peaks = load_peaks()
 
-    stack = build_stack(device, rank, world, args.layers)
+    stack = build_stack(device, rank, world, args.layers, fuse=not args.no_fuse)
     hidden = CFG["hidden"]
     sizes = [(CFG[kk] // (world if st == "row" else 1), CFG[nn_] // (world if st == "col" else 1))
              for _, kk, nn_, st in LINEARS]
@@ -400,10 +405,12 @@ def main():
                 "timing": "CUDA graph of the whole step, CUDA events around K replays, max over ranks",
             },
             "roofline": {
-                "kernel": "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL), 224 launches per step",
+                "kernel": "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL); "
+                          + ("one launch per QuantLinear" if args.no_fuse else
+                             "q/k/v and gate/up siblings share a launch: 4 launches per decoder layer"),
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                "algorithmic_bytes_per_launch": alg_bytes_step / n_lin, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes_step / (n_lin if args.no_fuse else 4 * args.layers), "traffic": None,
             },
             "prefill": {
                 "tokens": Mp, "ms_per_pass": ms_pre, "tflops": tflops, "iters": it_pre,
@@ -419,7 +426,7 @@ def main():
             "e2e": {"value": e2e_toks, "unit": "tok/s", "h2d_bytes_per_step": hidden * 2,
                     "d2h_bytes_per_step": hidden * 2,
                     "how": "pinned host x -> H2D -> graph replay of the 224 forward() calls -> D2H -> stream sync"},
-            "gpu_launches": n_lin,
+            "gpu_launches": n_lin if args.no_fuse else 4 * args.layers,
             "clocks": clocks,
             "finite_outputs": finite,
         }

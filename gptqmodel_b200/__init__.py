@@ -5,6 +5,6 @@ Public API:
     lib / check       the raw C-ABI (include/b2q.h) through ctypes
 """
 from ._lib import ABI_VERSION, B2QError, LIB_PATH, SYMBOLS, check, lib  # noqa: F401
-from .qlinear import B200QuantLinear  # noqa: F401
+from .qlinear import B200QuantLinear, SiblingGroup, fuse_siblings  # noqa: F401
 
-__all__ = ["B200QuantLinear", "lib", "check", "B2QError", "LIB_PATH", "SYMBOLS", "ABI_VERSION"]
+__all__ = ["B200QuantLinear", "fuse_siblings", "SiblingGroup", "lib", "check", "B2QError", "LIB_PATH", "SYMBOLS", "ABI_VERSION"]

@@ -160,6 +160,21 @@ int b2q_decode(const void* x, const void* packed, const void* scales, const int3
   return check_cuda(launch_decode(a), "b2q_decode");
 }
 
+int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const void* const* scales,
+                     const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* N, int M, int K,
+                     int bits, int group_size, int dtype, void* stream) {
+  if (x == nullptr || packed == nullptr || scales == nullptr || qzeros == nullptr || bias == nullptr ||
+      out == nullptr || N == nullptr || nsets < 1) {
+    set_error("b2q_decode_multi: null pointer argument");
+    return -2;
+  }
+  int v = validate("b2q_decode_multi", x, packed[0], scales[0], out[0], M, K, N[0], bits, group_size, dtype);
+  if (v != 0) return v;
+  MmArgs a = make_args(x, packed[0], scales[0], qzeros[0], nullptr, bias[0], out[0], M, K, N[0], bits, group_size,
+                       dtype, nullptr, 0, stream);
+  return check_cuda(launch_decode_multi(a, nsets, packed, scales, qzeros, bias, out, N), "b2q_decode_multi");
+}
+
 int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
              const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
              size_t workspace_bytes, void* stream) {

@@ -105,12 +105,56 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
   return v;
 }
 
+// Up to DEC_MAX_SETS weight sets that consume the SAME activations (q/k/v, gate/up: "sibling" QuantLinears) are served
+// by one launch: the 32-feature tiles of all sets form one index space (tile_end = running totals).
+constexpr int DEC_MAX_SETS = 3;
+struct DecSets {
+  int nsets;
+  int tile_end[DEC_MAX_SETS];
+  int N[DEC_MAX_SETS];
+  const uint4* packed[DEC_MAX_SETS];
+  const void* scales[DEC_MAX_SETS];
+  const uint32_t* qzeros[DEC_MAX_SETS];
+  const void* bias[DEC_MAX_SETS];
+  void* out[DEC_MAX_SETS];
+};
+
+template <typename T>
+struct TileRef {
+  const uint4* w;
+  const T* sc;
+  const uint32_t* zq;
+  const T* bias;
+  T* out;
+  int N, nt;
+};
+
+template <typename T>
+__device__ __forceinline__ TileRef<T> resolve_tile(const DecSets& S, int gt) {
+  int s = 0, start = 0;
+  if (S.nsets > 1 && gt >= S.tile_end[0]) {
+    s = 1;
+    start = S.tile_end[0];
+    if (S.nsets > 2 && gt >= S.tile_end[1]) {
+      s = 2;
+      start = S.tile_end[1];
+    }
+  }
+  TileRef<T> r;
+  r.w = S.packed[s];
+  r.sc = reinterpret_cast<const T*>(S.scales[s]);
+  r.zq = S.qzeros[s];
+  r.bias = reinterpret_cast<const T*>(S.bias[s]);
+  r.out = reinterpret_cast<T*>(S.out[s]);
+  r.N = S.N[s];
+  r.nt = gt - start;
+  return r;
+}
+
 template <typename T, bool ASYM, bool G64>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
-    decode_kernel(const uint4* __restrict__ packed, const T* __restrict__ scales, const uint32_t* __restrict__ qzeros,
-                  const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ bias,
-                  T* __restrict__ out, int M, int K, int N, int gsh, int qpc, int max_tiles,
-                  unsigned long long* __restrict__ trace) {
+    decode_kernel(const __grid_constant__ DecSets S, const int32_t* __restrict__ perm, const T* __restrict__ x, int M,
+                  int K, int gsh, int qpc, int max_tiles, unsigned long long* __restrict__ trace) {
   using E = ET<T>;
   extern __shared__ __align__(128) uint8_t dsm[];
   // optional phase timestamps (debug): trace[blockIdx.x * 16 + slot] = %globaltimer (ns)
@@ -126,8 +170,9 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   //               part[max_tiles][8][32] | mbarriers[nwarps][DEC_STAGES]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int NT = N >> 5, FT = N >> 4, C = gridDim.x;
-  const int ntiles = (blockIdx.x < NT) ? (NT - blockIdx.x + C - 1) / C : 0;  // tiles of this CTA
+  const int C = gridDim.x;
+  const int TT = S.tile_end[S.nsets - 1];                                      // tiles of all sets
+  const int ntiles = ((int)blockIdx.x < TT) ? (TT - (int)blockIdx.x + C - 1) / C : 0;  // tiles of this CTA
   const int nquads = K >> 7;
   const int q0 = blockIdx.y * qpc;
   const int q1 = min(q0 + qpc, nquads);
@@ -141,37 +186,80 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   int* fin = reinterpret_cast<int*>(part + max_tiles * 256) + nwarps * DEC_STAGES * 2;  // fin[2] after the mbarriers
   if (threadIdx.x == 0) fin[0] = fin[1] = 0;
   const bool PERM = perm != nullptr;
-  const size_t kb_stride = (size_t)FT * 32;
 
   // ---- 1. the first DEC_STAGES quads of this warp requested before anything else -----------------
   const int nq = (q0 + warp < q1) ? (q1 - q0 - warp + nwarps - 1) / nwarps : 0;  // quads per tile for this warp
   const int U = ntiles * nq;                                                     // units of this warp
-  // running source pointer of the next unit to issue (lane 0): quads of a tile are 2*nwarps k-blocks apart, tiles C*64 uint4
-  const uint4* iss_tile = packed + ((size_t)(2 * (q0 + warp)) * FT + 2 * blockIdx.x) * 32;
-  const uint4* iss_src = iss_tile;
-  const size_t quad_step = (size_t)(2 * nwarps) * kb_stride;
-  int iss_q = 0, iss_u = 0;
+  // issue cursor (lane 0): quads of a tile are 2*nwarps k-blocks apart; the tile -> (weight set, local tile) mapping is
+  // resolved once per tile
+  const uint4* iss_src = nullptr;
+  size_t iss_kbs = 0;  // k-block stride (uint4) of the set being issued
+  int iss_q = 0, iss_u = 0, iss_ti = 0;
+  auto iss_begin_tile = [&]() {
+    const TileRef<T> r = resolve_tile<T>(S, (int)blockIdx.x + iss_ti * C);
+    iss_kbs = (size_t)(r.N >> 4) * 32;
+    iss_src = r.w + (size_t)(2 * (q0 + warp)) * iss_kbs + (size_t)(2 * r.nt) * 32;
+  };
+  auto iss_one = [&](uint32_t dst, uint32_t bar) {
+    issue_quad(dst, bar, iss_src, iss_kbs);
+    ++iss_u;
+    if (++iss_q == nq) {
+      iss_q = 0;
+      ++iss_ti;
+      if (iss_u < U) iss_begin_tile();
+    } else {
+      iss_src += (size_t)(2 * nwarps) * iss_kbs;
+    }
+  };
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < DEC_STAGES; ++i) mbar_init(bars + 8 * i, 1);
     fence_mbar_init();
+    if (U > 0) iss_begin_tile();
 #pragma unroll
-    for (int i = 0; i < DEC_STAGES; ++i) {
-      if (iss_u < U) {
-        issue_quad(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i, iss_src, kb_stride);
-        ++iss_u;
-        if (++iss_q == nq) {
-          iss_q = 0;
-          iss_tile += (size_t)C * 64;
-          iss_src = iss_tile;
-        } else {
-          iss_src += quad_step;
-        }
+    for (int i = 0; i < DEC_STAGES; ++i)
+      if (iss_u < U) iss_one(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i);
+  }
+  // scale / zero prefetch cursor (all lanes): this lane's 4 feature rows are +0, +8, +16, +24 from sc_next
+  const int gstep = (2 * nwarps) >> gsh;         // groups between consecutive quads of this warp
+  const int g_first = (2 * (q0 + warp)) >> gsh;  // group of this warp's first quad in every tile
+  const T* sc_next = nullptr;
+  const uint32_t* zq_next = nullptr;
+  int pre_q = 0, pre_ti = 0, pre_N = 0;
+  auto pre_begin_tile = [&]() {
+    const TileRef<T> r = resolve_tile<T>(S, (int)blockIdx.x + pre_ti * C);
+    pre_N = r.N;
+    sc_next = r.sc + (size_t)g_first * r.N + r.nt * 32 + g;
+    if (ASYM) zq_next = r.zq + (size_t)g_first * (r.N >> 3) + r.nt * 4;
+  };
+  auto fetch_scales = [&](DScale<ASYM, G64>& d) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      d.s[0][i] = *reinterpret_cast<const uint16_t*>(sc_next + i * 8);
+      if (ASYM) d.zw[0][i] = zq_next[i];
+    }
+    if (G64) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        d.s[G64 ? 1 : 0][i] = *reinterpret_cast<const uint16_t*>(sc_next + (size_t)pre_N + i * 8);
+        if (ASYM) d.zw[G64 ? 1 : 0][i] = zq_next[(pre_N >> 3) + i];
       }
     }
-  }
+    // advance to the next unit
+    if (++pre_q == nq) {
+      pre_q = 0;
+      ++pre_ti;
+      if (pre_ti < ntiles) pre_begin_tile();
+    } else {
+      sc_next += (size_t)gstep * pre_N;
+      if (ASYM) zq_next += (size_t)gstep * (pre_N >> 3);
+    }
+  };
   DScale<ASYM, G64> cur;
-  if (U > 0) load_dscale<T, ASYM, G64>(cur, scales, qzeros, q0 + warp, gsh, N, blockIdx.x * 32 + g);
+  if (U > 0) {
+    pre_begin_tile();
+    fetch_scales(cur);
+  }
 
   // PDL: let the next kernel start its own weight prefetch; wait for the producer of x only now.
   stamp(1);
@@ -230,45 +318,12 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const uint32_t xf_a0 = smem_u32(sx) + (uint32_t)((g * kspan + t * 16 + warp * 128) * 2);
   const uint32_t xs_a0 = smem_u32(xsum) + (uint32_t)((2 * t + warp * 16) * 4);
   const uint32_t xf_qstep = (uint32_t)nwarps * 256u, xs_qstep = (uint32_t)nwarps * 64u;
-  const int gstep = (2 * nwarps) >> gsh;                    // groups between consecutive quads of this warp
-  const int g_first = (2 * (q0 + warp)) >> gsh;             // group of this warp's first quad in every tile
-  const T* sc_tile = scales + (size_t)g_first * N + blockIdx.x * 32 + g;
-  const uint32_t* zq_tile = ASYM ? qzeros + (size_t)g_first * (N >> 3) + blockIdx.x * 4 : nullptr;
-  const T* sc_next = sc_tile;   // scale pointer of the NEXT unit to prefetch
-  const uint32_t* zq_next = zq_tile;
-  int pre_q = 0;                // quad-in-tile of the next unit to prefetch
-  auto advance_prefetch = [&]() {
-    if (++pre_q == nq) {
-      pre_q = 0;
-      sc_tile += (size_t)C * 32;
-      sc_next = sc_tile;
-      if (ASYM) {
-        zq_tile += (size_t)C * 4;
-        zq_next = zq_tile;
-      }
-    } else {
-      sc_next += (size_t)gstep * N;
-      if (ASYM) zq_next += (size_t)gstep * (N >> 3);
-    }
-  };
-  auto fetch_scales = [&](DScale<ASYM, G64>& d) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      d.s[0][i] = *reinterpret_cast<const uint16_t*>(sc_next + i * 8);
-      if (ASYM) d.zw[0][i] = zq_next[i];
-    }
-    if (G64) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        d.s[G64 ? 1 : 0][i] = *reinterpret_cast<const uint16_t*>(sc_next + (size_t)N + i * 8);
-        if (ASYM) d.zw[G64 ? 1 : 0][i] = zq_next[(N >> 3) + i];
-      }
-    }
-  };
-  advance_prefetch();  // unit 0 was fetched in the prologue (cur)
   int u = 0;
   for (int ti = 0; ti < ntiles; ++ti) {
-    const int nt = blockIdx.x + ti * C;
+    const TileRef<T> tr = resolve_tile<T>(S, (int)blockIdx.x + ti * C);
+    const int nt = tr.nt, N = tr.N;
+    const T* bias = tr.bias;
+    T* out = tr.out;
     float tot[2][4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -278,10 +333,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     uint32_t xf_a = xf_a0, xs_a = xs_a0;
     for (int qi = 0; qi < nq; ++qi, ++u, xf_a += xf_qstep, xs_a += xs_qstep) {
       DScale<ASYM, G64> nxt;
-      if (u + 1 < U) {
-        fetch_scales(nxt);
-        advance_prefetch();
-      }
+      if (u + 1 < U) fetch_scales(nxt);
       const int st = u & (DEC_STAGES - 1);
       mbar_wait(bars + 8 * st, (uint32_t)(u / DEC_STAGES) & 1u);
       const uint32_t wq_a = ring_a + st * DEC_QUAD_BYTES;
@@ -346,17 +398,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       }
       // recycle the stage for the next not-yet-issued unit (all lanes have finished reading it)
       __syncwarp();
-      if (lane == 0 && iss_u < U) {
-        issue_quad(ring_a + st * DEC_QUAD_BYTES, bars + 8 * st, iss_src, kb_stride);
-        ++iss_u;
-        if (++iss_q == nq) {
-          iss_q = 0;
-          iss_tile += (size_t)C * 64;  // next tile: 2 feature tiles x 32 uint4 per CTA stride
-          iss_src = iss_tile;
-        } else {
-          iss_src += quad_step;
-        }
-      }
+      if (lane == 0 && iss_u < U) iss_one(ring_a + st * DEC_QUAD_BYTES, bars + 8 * st);
       if (u + 1 < U) cur = nxt;
     }
 
@@ -398,7 +440,10 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     cluster_sync_all();
     const uint32_t rank = cluster_ctarank();
     for (int ti = (int)rank; ti < ntiles; ti += (int)nrank) {
-      const int nt = blockIdx.x + ti * C;
+      const TileRef<T> tr = resolve_tile<T>(S, (int)blockIdx.x + ti * C);
+      const int nt = tr.nt, N = tr.N;
+      const T* bias = tr.bias;
+      T* out = tr.out;
       for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int acc = i >> 5, ln = i & 31;
         const int m = 2 * (ln & 3) + (acc & 1);
@@ -428,9 +473,9 @@ static size_t decode_smem(int M, int warps, int qpc, int max_tiles) {
          (size_t)2 * warps * 256 * 4 + (size_t)max_tiles * 256 * 4 + (size_t)warps * DEC_STAGES * 8 + 16;
 }
 
-// Pick (C tiles-columns, ks split-K ranks, warps) minimising the critical path in "quads per warp" on ~148 CTAs.
-static bool decode_config(const MmArgs& a, DecodeCfg& best) {
-  const int quads = a.K / 128, NT = a.N / 32;
+// Pick (C tile-columns, ks split-K ranks, warps) minimising the critical path in "quads per warp" on ~148 CTAs.
+static bool decode_config(const MmArgs& a, int NT, DecodeCfg& best) {
+  const int quads = a.K / 128;
   const int SMS = 148;
   double best_cost = 1e30;
   bool found = false;
@@ -446,11 +491,11 @@ static bool decode_config(const MmArgs& a, DecodeCfg& best) {
       const int max_tiles = (NT + C - 1) / C;
       const size_t smem = decode_smem(a.M, warps, qpc, ks > 1 ? max_tiles : 0);
       if (smem > 200 * 1024) continue;
-      const int qpw = (qpc + warps - 1) / warps;          // quads per warp per tile
-      // critical path: tiles * quads-per-warp, plus a per-tile barrier and a fixed per-kernel part
+      const int qpw = (qpc + warps - 1) / warps;  // quads per warp per tile
       // calibrated on the B200 sweep (profiles/r01_decode_notes.md): per tile = quads/warp + barrier epilogue,
       // split-K adds a cluster barrier + DSMEM pass, fewer warps hide less latency
-      const double cost = (double)max_tiles * (qpw + 0.35) + (ks > 1 ? 0.6 : 0.0) + (16 - warps) * 0.04 * max_tiles * qpw;
+      const double cost =
+          (double)max_tiles * (qpw + 0.35) + (ks > 1 ? 0.6 : 0.0) + (16 - warps) * 0.04 * max_tiles * qpw;
       if (cost < best_cost) {
         best_cost = cost;
         best = DecodeCfg{C, ks, warps, qpc, ks > 1 ? max_tiles : 0, smem};
@@ -462,7 +507,7 @@ static bool decode_config(const MmArgs& a, DecodeCfg& best) {
 }
 
 template <typename T, bool ASYM, bool G64>
-static int launch_decode_t(const MmArgs& a, const DecodeCfg& c) {
+static int launch_decode_t(const MmArgs& a, const DecSets& sets, const DecodeCfg& c) {
   auto kern = decode_kernel<T, ASYM, G64>;
   if (c.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
@@ -485,9 +530,7 @@ static int launch_decode_t(const MmArgs& a, const DecodeCfg& c) {
   int gsh = 31;  // per-channel: every k-block is group 0
   if (a.group_size == 64) gsh = 0;
   else if (a.group_size == 128) gsh = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const uint4*)a.packed, (const T*)a.scales,
-                                     (const uint32_t*)a.qzeros, a.perm, (const T*)a.x, (const T*)a.bias, (T*)a.out,
-                                     a.M, a.K, a.N, gsh, c.qpc, c.max_tiles,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sets, a.perm, (const T*)a.x, a.M, a.K, gsh, c.qpc, c.max_tiles,
                                      (unsigned long long*)g_trace_ptr);
   return (int)e;
 }
@@ -497,25 +540,72 @@ bool decode_supported(const MmArgs& a) {
          (a.group_size == 64 || a.group_size == 128 || a.group_size == a.K);
 }
 
-int launch_decode(const MmArgs& a) {
-  if (!decode_supported(a)) {
-    set_error("b2q_decode: unsupported (bits=%d M=%d K=%d N=%d group=%d)", a.bits, a.M, a.K, a.N, a.group_size);
-    return -1;
-  }
+static int launch_decode_sets(const MmArgs& a, const DecSets& sets) {
   DecodeCfg c;
-  if (!decode_config(a, c)) {
+  if (!decode_config(a, sets.tile_end[sets.nsets - 1], c)) {
     set_error("b2q_decode: no configuration fits shared memory for M=%d K=%d (ks=%d warps=%d)", a.M, a.K, a.tune_ks,
               a.tune_warps);
     return -1;
   }
   const bool asym = a.qzeros != nullptr, g64 = a.group_size == 64;
-#define B2Q_DEC_CASE(T)                                                       \
-  (asym ? (g64 ? launch_decode_t<T, true, true>(a, c)                         \
-               : launch_decode_t<T, true, false>(a, c))                       \
-        : (g64 ? launch_decode_t<T, false, true>(a, c)                        \
-               : launch_decode_t<T, false, false>(a, c)))
+#define B2Q_DEC_CASE(T)                                                          \
+  (asym ? (g64 ? launch_decode_t<T, true, true>(a, sets, c)                      \
+               : launch_decode_t<T, true, false>(a, sets, c))                    \
+        : (g64 ? launch_decode_t<T, false, true>(a, sets, c)                     \
+               : launch_decode_t<T, false, false>(a, sets, c)))
   return a.dtype == 0 ? B2Q_DEC_CASE(__half) : B2Q_DEC_CASE(__nv_bfloat16);
 #undef B2Q_DEC_CASE
+}
+
+int launch_decode(const MmArgs& a) {
+  if (!decode_supported(a)) {
+    set_error("b2q_decode: unsupported (bits=%d M=%d K=%d N=%d group=%d)", a.bits, a.M, a.K, a.N, a.group_size);
+    return -1;
+  }
+  DecSets sets = {};
+  sets.nsets = 1;
+  sets.tile_end[0] = a.N / 32;
+  sets.N[0] = a.N;
+  sets.packed[0] = (const uint4*)a.packed;
+  sets.scales[0] = a.scales;
+  sets.qzeros[0] = (const uint32_t*)a.qzeros;
+  sets.bias[0] = a.bias;
+  sets.out[0] = a.out;
+  return launch_decode_sets(a, sets);
+}
+
+// Sibling QuantLinears (same x, same K / group size / symmetry, no act-order) in ONE launch.
+int launch_decode_multi(const MmArgs& a, int nsets, const void* const* packed, const void* const* scales,
+                        const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* Ns) {
+  if (nsets < 1 || nsets > DEC_MAX_SETS) {
+    set_error("b2q_decode_multi: nsets=%d out of range (1..%d)", nsets, DEC_MAX_SETS);
+    return -1;
+  }
+  DecSets sets = {};
+  sets.nsets = nsets;
+  int tiles = 0;
+  for (int i = 0; i < nsets; ++i) {
+    MmArgs ai = a;
+    ai.N = Ns[i];
+    if (!decode_supported(ai) || Ns[i] % 32 != 0 || packed[i] == nullptr || scales[i] == nullptr ||
+        out[i] == nullptr || ((qzeros[i] != nullptr) != (qzeros[0] != nullptr))) {
+      set_error("b2q_decode_multi: set %d unsupported (N=%d; all sets must share bits=4, K, group size and symmetry)", i,
+                Ns[i]);
+      return -1;
+    }
+    tiles += Ns[i] / 32;
+    sets.tile_end[i] = tiles;
+    sets.N[i] = Ns[i];
+    sets.packed[i] = (const uint4*)packed[i];
+    sets.scales[i] = scales[i];
+    sets.qzeros[i] = (const uint32_t*)qzeros[i];
+    sets.bias[i] = bias[i];
+    sets.out[i] = out[i];
+  }
+  for (int i = nsets; i < DEC_MAX_SETS; ++i) sets.tile_end[i] = tiles;
+  MmArgs a0 = a;
+  a0.qzeros = qzeros[0];
+  return launch_decode_sets(a0, sets);
 }
 
 }  // namespace b2q

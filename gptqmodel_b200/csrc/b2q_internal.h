@@ -30,6 +30,8 @@ int launch_permute_cols(const void* x, const int32_t* perm, void* out, int M, in
 int launch_gemv(const MmArgs& a);     // 8-bit, M == 1: CUDA-core FHFMA GEMV
 int launch_decode(const MmArgs& a);   // 4-bit, M <= 8: mma.sync decode tier
 bool decode_supported(const MmArgs& a);
+int launch_decode_multi(const MmArgs& a, int nsets, const void* const* packed, const void* const* scales,
+                        const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* Ns);
 int launch_gemm(const MmArgs& a);
 int launch_gemm2(const MmArgs& a, const void* x);
 int gemm_gshc(const MmArgs& a);  // 4-bit, CTA-pair (cta_group::2) tier; x already permuted

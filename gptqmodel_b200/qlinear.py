@@ -21,9 +21,73 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
+import ctypes
+
 from ._lib import B2QError, check, lib
 
 _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
+DECODE_MAX_M = 8
+
+
+class SiblingGroup:
+    """QuantLinears that consume the SAME activations (q/k/v, gate/up) served by ONE decode launch.
+
+    The first member called with a new `x` launches `b2q_decode_multi` for all members and parks the siblings'
+    outputs; each sibling's `forward(x)` then just picks its result up.  Every module keeps the reference's
+    per-module `forward(x) -> y` contract (results are bit-identical to separate calls); only the launch count
+    changes.  This is SURVEY.md §8 row f1 ("fused neighbours of the GEMM").
+    """
+
+    def __init__(self, members):
+        self.members = list(members)
+        self.key = None
+        self.pending = {}
+
+    def run(self, who, x2, M):
+        key = (x2.data_ptr(), x2._version, M, x2.dtype)
+        if self.key == key and id(who) in self.pending:
+            out = self.pending.pop(id(who))
+            if not self.pending:
+                self.key = None
+            return out
+        mods = self.members
+        n = len(mods)
+        K = who.in_features
+        outs = [torch.empty((M, m.out_features), dtype=x2.dtype, device=x2.device) for m in mods]
+        vp = ctypes.c_void_p * n
+        packed = vp(*[m.packed.data_ptr() for m in mods])
+        scales = vp(*[m._scales_for(x2.dtype).data_ptr() for m in mods])
+        zeros = vp(*[_ptr(m._zeros_dev) for m in mods])
+        bias = vp(*[_ptr(m._bias_for(x2.dtype)) for m in mods])
+        outp = vp(*[o.data_ptr() for o in outs])
+        Ns = (ctypes.c_int * n)(*[m.out_features for m in mods])
+        check(lib.b2q_decode_multi(x2.data_ptr(), n, packed, scales, zeros, bias, outp, Ns, M, K, who.bits,
+                                   who.group_size, _DTYPE_CODE[x2.dtype],
+                                   torch.cuda.current_stream(x2.device).cuda_stream), "b2q_decode_multi")
+        self.key = key
+        self.pending = {id(m): o for m, o in zip(mods, outs) if m is not who}
+        return outs[mods.index(who)]
+
+
+def fuse_siblings(mods) -> bool:
+    """Group post_init'ed B200QuantLinear modules that are always called with the same input (q/k/v or gate/up).
+    Returns False (and changes nothing) if the set cannot share a launch."""
+    mods = list(mods)
+    if not (2 <= len(mods) <= 3):
+        return False
+    m0 = mods[0]
+    for m in mods:
+        if not isinstance(m, B200QuantLinear) or not m._prepacked or m.bits != 4 or m.perm is not None:
+            return False
+        if (m.in_features, m.group_size, m._is_sym, m.packed.device, m.scales.dtype) != (
+                m0.in_features, m0.group_size, m0._is_sym, m0.packed.device, m0.scales.dtype):
+            return False
+        if m.in_features % 128 != 0 or m.group_size not in (64, 128, m.in_features) or m.adapter:
+            return False
+    grp = SiblingGroup(mods)
+    for m in mods:
+        m._siblings = grp
+    return True
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -91,6 +155,7 @@ class B200QuantLinear(nn.Module):
         self._qzeros_format = 2
         self._prepacked = False
         self._scales_cache = {}
+        self._siblings = None
 
         K, N, G = in_features, out_features, math.ceil(in_features / self.group_size)
         # checkpoint-shaped, non-trainable Parameters (what Marlin/Swordfish register: swordfish.py:108-148)
@@ -251,6 +316,8 @@ class B200QuantLinear(nn.Module):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         M = x2.shape[0]
+        if self._siblings is not None and 1 <= M <= DECODE_MAX_M:
+            return self._siblings.run(self, x2, M).reshape(out_shape)
         out = torch.empty((M, N), dtype=x.dtype, device=x.device)
         if M == 0:
             return out.reshape(out_shape)

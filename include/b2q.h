@@ -75,6 +75,14 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
              const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
              size_t workspace_bytes, void* stream);
 
+/* Sibling layers that consume the SAME activations (q/k/v, gate/up; module order in the reference:
+ * gptqmodel/models/definitions/llama.py:17-27) in ONE decode launch: nsets <= 3 weight sets given as HOST arrays of
+ * device pointers; all sets share M <= 8, K, bits = 4, group_size, dtype and symmetry (qzeros all NULL or all non-NULL),
+ * no act-order.  out[i] is [M, N[i]].  Same arithmetic as nsets separate b2q_decode calls (bit-identical results). */
+int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const void* const* scales,
+                     const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* N, int M, int K,
+                     int bits, int group_size, int dtype, void* stream);
+
 /* Debug: device buffer (>= 148*16 uint64) receiving %globaltimer phase stamps of the decode kernel; NULL = off. */
 void b2q_debug_set_trace(void* device_buffer);
 

@@ -261,3 +261,33 @@ def test_cuda_graph_capture_and_stream():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(y1, ref1) and torch.equal(y8, ref8)
+
+
+@pytest.mark.parametrize("sym,gs,bias", [(True, 128, False), (False, 64, True), (True, -1, False)])
+def test_sibling_fusion_bit_identical(sym, gs, bias):
+    """q/k/v-style siblings in ONE launch (b2q_decode_multi) == three separate forwards, bit for bit."""
+    from gptqmodel_b200 import fuse_siblings
+    K = 1024
+    Ls = [make_layer(K, n, group_size=gs, sym=sym, bias=bias, seed=20 + i) for i, n in enumerate((1024, 256, 512))]
+    mods = [_module(L) for L in Ls]
+    gen = torch.Generator().manual_seed(3)
+    for M in (1, 3, 8):
+        x = (torch.randn(M, K, generator=gen) * 0.5).to(torch.float16).to(DEV)
+        sep = [m(x).clone() for m in mods]
+        assert fuse_siblings(mods)
+        fused = [m(x) for m in mods]          # first call launches for all three, the others pick up
+        for a, b, L in zip(sep, fused, Ls):
+            assert torch.equal(a, b)
+            assert_close_rel(b, oracle_forward(L, x.cpu()), 1e-3, f"fused M={M}")
+        # a different input invalidates the parked outputs; calling only one sibling still works
+        x2 = (x * 0.5).to(torch.float16)
+        assert torch.equal(mods[1](x2), mods[1].__class__.forward(mods[1], x2))
+        big = (torch.randn(64, K, generator=gen) * 0.5).to(torch.float16).to(DEV)   # M > 8: falls through to the GEMM tier
+        assert_close_rel(mods[0](big), oracle_forward(Ls[0], big.cpu()), 1e-3, "fused M=64")
+        for m in mods:
+            m._siblings = None
+    # refused combinations
+    ao = _module(make_layer(K, 256, group_size=64, desc_act=True, seed=30))
+    assert not fuse_siblings([mods[0], ao])
+    other_k = _module(make_layer(512, 256, seed=31))
+    assert not fuse_siblings([mods[0], other_k])
