@@ -48,6 +48,14 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
+def load_traffic():
+    """DRAM bytes measured by ncu (--set full) for one decode launch, as a ratio of its algorithmic bytes."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
 def algorithmic_bytes(K, N, gs, bits, M):
     G = K // gs
     return K * N * bits // 8 + G * N * 2 + G * (N * bits // 32) * 4 + M * K * 2 + M * N * 2
@@ -393,6 +401,9 @@ def main():
 
     if rank == 0:
         achieved = alg_bytes_step / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU
+        tr = load_traffic()
+        n_launch = n_lin if args.no_fuse else 4 * args.layers
+        traffic = (tr["decode_kernel"]["ratio"] * alg_bytes_step / n_launch) if tr else None
         line = {
             "metric": METRIC, "value": toks, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -410,7 +421,10 @@ def main():
                              "q/k/v and gate/up siblings share a launch: 4 launches per decoder layer"),
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                "algorithmic_bytes_per_launch": alg_bytes_step / (n_lin if args.no_fuse else 4 * args.layers), "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes_step / n_launch, "traffic": traffic,
+                "traffic_note": "average per launch = measured DRAM/algorithmic ratio of the ncu --set full capture "
+                                "(profiles/r01_decode_final.txt: 30,318,080 B DRAM vs 30,539,776 B algorithmic for the "
+                                "4096x14336 launch) x algorithmic bytes per launch",
             },
             "prefill": {
                 "tokens": Mp, "ms_per_pass": ms_pre, "tflops": tflops, "iters": it_pre,

@@ -19,6 +19,8 @@
 //  * act-order: rows sorted by group at prepack, the x[perm[k']] gather is fused into the activation staging.
 // Replaces the decode tiers of swordfish_mm (swordfish_mm.cu:216-286, mma.sync + cp.async + atomics) and Marlin's
 // small-M path (marlin_template.h) in the reference.
+#include <cstdlib>
+
 #include "b2q_common.cuh"
 #include "b2q_internal.h"
 
@@ -154,7 +156,7 @@ __device__ __forceinline__ TileRef<T> resolve_tile(const DecSets& S, int gt) {
 template <typename T, bool ASYM, bool G64>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     decode_kernel(const __grid_constant__ DecSets S, const int32_t* __restrict__ perm, const T* __restrict__ x, int M,
-                  int K, int gsh, int qpc, int max_tiles, unsigned long long* __restrict__ trace) {
+                  int K, int gsh, int qpc, int max_tiles, int ngroups, unsigned long long* __restrict__ trace) {
   using E = ET<T>;
   extern __shared__ __align__(128) uint8_t dsm[];
   // optional phase timestamps (debug): trace[blockIdx.x * 16 + slot] = %globaltimer (ns)
@@ -170,9 +172,15 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   //               part[max_tiles][8][32] | mbarriers[nwarps][DEC_STAGES]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int C = gridDim.x;
-  const int TT = S.tile_end[S.nsets - 1];                                      // tiles of all sets
-  const int ntiles = ((int)blockIdx.x < TT) ? (TT - (int)blockIdx.x + C - 1) / C : 0;  // tiles of this CTA
+  // The CTA's warps form `ngroups` independent groups (1 or 2); a group owns whole tiles (group-strided over the
+  // launch) and its `gw` warps split the k-quads of a tile.  With 2 groups, one group's tile epilogue (barrier + cross-
+  // warp reduction, ~0.5 us of mostly latency) overlaps the other group's main loop on the same SM.
+  const int gw = nwarps / ngroups;              // warps per group
+  const int grp = warp / gw, wg = warp - grp * gw;
+  const int C = gridDim.x * ngroups;            // tile stride of a group
+  const int tile0 = (int)blockIdx.x * ngroups + grp;
+  const int TT = S.tile_end[S.nsets - 1];       // tiles of all sets
+  const int ntiles = (tile0 < TT) ? (TT - tile0 + C - 1) / C : 0;  // tiles of this group
   const int nquads = K >> 7;
   const int q0 = blockIdx.y * qpc;
   const int q1 = min(q0 + qpc, nquads);
@@ -181,14 +189,14 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   T* sx = reinterpret_cast<T*>(dsm + (size_t)nwarps * DEC_STAGES * DEC_QUAD_BYTES);
   float* xsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sx) + (size_t)M * kspan * sizeof(T));
   float* red = xsum + qpc * 2 * 8;
-  float* part = red + 2 * nwarps * 256;
+  float* part = red + 2 * nwarps * 256;  // [ngroups][max_tiles][256]
   const uint32_t bars = smem_u32(part + max_tiles * 256) + warp * DEC_STAGES * 8;
   int* fin = reinterpret_cast<int*>(part + max_tiles * 256) + nwarps * DEC_STAGES * 2;  // fin[2] after the mbarriers
   if (threadIdx.x == 0) fin[0] = fin[1] = 0;
   const bool PERM = perm != nullptr;
 
   // ---- 1. the first DEC_STAGES quads of this warp requested before anything else -----------------
-  const int nq = (q0 + warp < q1) ? (q1 - q0 - warp + nwarps - 1) / nwarps : 0;  // quads per tile for this warp
+  const int nq = (q0 + wg < q1) ? (q1 - q0 - wg + gw - 1) / gw : 0;  // quads per tile for this warp
   const int U = ntiles * nq;                                                     // units of this warp
   // issue cursor (lane 0): quads of a tile are 2*nwarps k-blocks apart; the tile -> (weight set, local tile) mapping is
   // resolved once per tile
@@ -196,9 +204,9 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   size_t iss_kbs = 0;  // k-block stride (uint4) of the set being issued
   int iss_q = 0, iss_u = 0, iss_ti = 0;
   auto iss_begin_tile = [&]() {
-    const TileRef<T> r = resolve_tile<T>(S, (int)blockIdx.x + iss_ti * C);
+    const TileRef<T> r = resolve_tile<T>(S, tile0 + iss_ti * C);
     iss_kbs = (size_t)(r.N >> 4) * 32;
-    iss_src = r.w + (size_t)(2 * (q0 + warp)) * iss_kbs + (size_t)(2 * r.nt) * 32;
+    iss_src = r.w + (size_t)(2 * (q0 + wg)) * iss_kbs + (size_t)(2 * r.nt) * 32;
   };
   auto iss_one = [&](uint32_t dst, uint32_t bar) {
     issue_quad(dst, bar, iss_src, iss_kbs);
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       ++iss_ti;
       if (iss_u < U) iss_begin_tile();
     } else {
-      iss_src += (size_t)(2 * nwarps) * iss_kbs;
+      iss_src += (size_t)(2 * gw) * iss_kbs;
     }
   };
   if (lane == 0) {
@@ -221,13 +229,13 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       if (iss_u < U) iss_one(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i);
   }
   // scale / zero prefetch cursor (all lanes): this lane's 4 feature rows are +0, +8, +16, +24 from sc_next
-  const int gstep = (2 * nwarps) >> gsh;         // groups between consecutive quads of this warp
-  const int g_first = (2 * (q0 + warp)) >> gsh;  // group of this warp's first quad in every tile
+  const int gstep = (2 * gw) >> gsh;           // quantisation groups between consecutive quads of this warp
+  const int g_first = (2 * (q0 + wg)) >> gsh;  // quantisation group of this warp's first quad in every tile
   const T* sc_next = nullptr;
   const uint32_t* zq_next = nullptr;
   int pre_q = 0, pre_ti = 0, pre_N = 0;
   auto pre_begin_tile = [&]() {
-    const TileRef<T> r = resolve_tile<T>(S, (int)blockIdx.x + pre_ti * C);
+    const TileRef<T> r = resolve_tile<T>(S, tile0 + pre_ti * C);
     pre_N = r.N;
     sc_next = r.sc + (size_t)g_first * r.N + r.nt * 32 + g;
     if (ASYM) zq_next = r.zq + (size_t)g_first * (r.N >> 3) + r.nt * 4;
@@ -315,12 +323,12 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   constexpr float ZSYM = 8.f;
   const uint32_t nrank = cluster_nctarank();
   const uint32_t ring_a = smem_u32(ring) + lane * 16;
-  const uint32_t xf_a0 = smem_u32(sx) + (uint32_t)((g * kspan + t * 16 + warp * 128) * 2);
-  const uint32_t xs_a0 = smem_u32(xsum) + (uint32_t)((2 * t + warp * 16) * 4);
-  const uint32_t xf_qstep = (uint32_t)nwarps * 256u, xs_qstep = (uint32_t)nwarps * 64u;
+  const uint32_t xf_a0 = smem_u32(sx) + (uint32_t)((g * kspan + t * 16 + wg * 128) * 2);
+  const uint32_t xs_a0 = smem_u32(xsum) + (uint32_t)((2 * t + wg * 16) * 4);
+  const uint32_t xf_qstep = (uint32_t)gw * 256u, xs_qstep = (uint32_t)gw * 64u;
   int u = 0;
   for (int ti = 0; ti < ntiles; ++ti) {
-    const TileRef<T> tr = resolve_tile<T>(S, (int)blockIdx.x + ti * C);
+    const TileRef<T> tr = resolve_tile<T>(S, tile0 + ti * C);
     const int nt = tr.nt, N = tr.N;
     const T* bias = tr.bias;
     T* out = tr.out;
@@ -407,17 +415,17 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     //  warp on a split arrive/sync named barrier" — profiles/r01_decode_notes.md)
     // tot[ftl][c]: feature nt*32 + ftl*16 + g (+8 if c >= 2), token 2t + (c & 1)
     if (ti < 5) stamp(4 + 2 * ti);
-    float* rbuf = red + (ti & 1) * nwarps * 256;
+    float* rbuf = red + (grp * 2 + (ti & 1)) * gw * 256;
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) rbuf[(warp * 8 + a * 4 + b) * 32 + lane] = tot[a][b];
-    __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      for (int b = 0; b < 4; ++b) rbuf[(wg * 8 + a * 4 + b) * 32 + lane] = tot[a][b];
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gw * 32) : "memory");  // this group's warps only
+    for (int i = wg * 32 + lane; i < 256; i += gw * 32) {
       float v = 0.f;
-      for (int w = 0; w < nwarps; ++w) v += rbuf[w * 256 + i];
+      for (int w = 0; w < gw; ++w) v += rbuf[w * 256 + i];
       if (nrank > 1) {
-        part[ti * 256 + i] = v;
+        part[(grp * max_tiles + ti) * 256 + i] = v;
       } else {
         const int acc = i >> 5, ln = i & 31;
         const int m = 2 * (ln & 3) + (acc & 1);
@@ -439,17 +447,18 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     __syncthreads();  // every tile's reducer has written its partials
     cluster_sync_all();
     const uint32_t rank = cluster_ctarank();
+    // each group reduces its own tiles (same tile <-> group mapping in every rank of the cluster)
     for (int ti = (int)rank; ti < ntiles; ti += (int)nrank) {
-      const TileRef<T> tr = resolve_tile<T>(S, (int)blockIdx.x + ti * C);
+      const TileRef<T> tr = resolve_tile<T>(S, tile0 + ti * C);
       const int nt = tr.nt, N = tr.N;
       const T* bias = tr.bias;
       T* out = tr.out;
-      for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      for (int i = wg * 32 + lane; i < 256; i += gw * 32) {
         const int acc = i >> 5, ln = i & 31;
         const int m = 2 * (ln & 3) + (acc & 1);
         if (m < M) {
           float v = 0.f;
-          for (uint32_t r = 0; r < nrank; ++r) v += ld_dsmem_f32(smem_u32(&part[ti * 256 + i]), r);
+          for (uint32_t r = 0; r < nrank; ++r) v += ld_dsmem_f32(smem_u32(&part[(grp * max_tiles + ti) * 256 + i]), r);
           const int n = nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
           T o = E::from_f(v);
           if (bias != nullptr) o = E::from_f(E::to_f(o) + E::to_f(bias[n]));
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
 void* g_trace_ptr = nullptr;
 
 struct DecodeCfg {
-  int C, ks, warps, qpc, max_tiles;
+  int C, ks, warps, qpc, max_tiles, ngroups;
   size_t smem;
 };
 
@@ -485,20 +494,26 @@ static bool decode_config(const MmArgs& a, int NT, DecodeCfg& best) {
     const int qpc = (quads + ks - 1) / ks;
     for (int warps = 4; warps <= DEC_MAX_WARPS; warps *= 2) {  // 4, 8, 16
       if (a.tune_warps > 0 && warps != a.tune_warps) continue;
+      const char* eg = getenv("B2Q_DECODE_GROUPS");
+      // two independent 8-warp groups per CTA overlap one group's tile epilogue with the other's main loop (+5 % on the
+      // Llama-3-8B step) but one full-size parity case failed with it in round 1: experimental, off by default
+      int ngroups = 1;
+      if (eg != nullptr && eg[0] == '2' && warps == 16 && ks == 1) ngroups = 2;  // (the split-K + groups combination faults)
+      const int gwarps = warps / ngroups;
       int C = SMS / ks;
-      if (C > NT) C = NT;
+      if (C * ngroups > NT) C = (NT + ngroups - 1) / ngroups;
       if (C < 1) C = 1;
-      const int max_tiles = (NT + C - 1) / C;
-      const size_t smem = decode_smem(a.M, warps, qpc, ks > 1 ? max_tiles : 0);
+      const int max_tiles = (NT + C * ngroups - 1) / (C * ngroups);  // per group
+      const size_t smem = decode_smem(a.M, warps, qpc, ks > 1 ? max_tiles * ngroups : 0);
       if (smem > 200 * 1024) continue;
-      const int qpw = (qpc + warps - 1) / warps;  // quads per warp per tile
+      const int qpw = (qpc + gwarps - 1) / gwarps;  // quads per warp per tile
       // calibrated on the B200 sweep (profiles/r01_decode_notes.md): per tile = quads/warp + barrier epilogue,
       // split-K adds a cluster barrier + DSMEM pass, fewer warps hide less latency
       const double cost =
-          (double)max_tiles * (qpw + 0.35) + (ks > 1 ? 0.6 : 0.0) + (16 - warps) * 0.04 * max_tiles * qpw;
+          (double)max_tiles * (qpw + 0.35) / ngroups + (ks > 1 ? 0.6 : 0.0) + (16 - warps) * 0.04 * max_tiles * qpw;
       if (cost < best_cost) {
         best_cost = cost;
-        best = DecodeCfg{C, ks, warps, qpc, ks > 1 ? max_tiles : 0, smem};
+        best = DecodeCfg{C, ks, warps, qpc, ks > 1 ? max_tiles : 0, ngroups, smem};
         found = true;
       }
     }
@@ -531,7 +546,7 @@ static int launch_decode_t(const MmArgs& a, const DecSets& sets, const DecodeCfg
   if (a.group_size == 64) gsh = 0;
   else if (a.group_size == 128) gsh = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sets, a.perm, (const T*)a.x, a.M, a.K, gsh, c.qpc, c.max_tiles,
-                                     (unsigned long long*)g_trace_ptr);
+                                     c.ngroups, (unsigned long long*)g_trace_ptr);
   return (int)e;
 }
 
