@@ -291,3 +291,35 @@ def test_sibling_fusion_bit_identical(sym, gs, bias):
     assert not fuse_siblings([mods[0], ao])
     other_k = _module(make_layer(512, 256, seed=31))
     assert not fuse_siblings([mods[0], other_k])
+
+
+@pytest.mark.parametrize("K,N,kind", [
+    (8192, 1024, "q_proj column shard"), (1024, 8192, "o_proj row shard"),
+    (8192, 3584, "gate/up column shard"), (3584, 8192, "down_proj row shard"),
+])
+def test_llama3_70b_tp8_shard_shapes(K, N, kind):
+    """BASELINE configs[3]: the per-rank QuantLinear shapes of Llama-3-70B under TP-8, decode + prefill."""
+    L = random_layer(K, N, bits=4, group_size=128, sym=True, seed=K * 7 + N)
+    mod = _module(L)
+    W = oracle.dequantize_weight(L["qweight"].to(DEV), L["qzeros"].to(DEV), L["scales"].to(DEV),
+                                 L["g_idx"].to(DEV), 4).float()
+    torch.manual_seed(2)
+    x = (torch.randn(300, K, device=DEV) * 0.5).to(torch.float16)
+    ref = (x.float() @ W).to(torch.float16)
+    assert_close_rel(mod(x), ref, 1e-3, f"{kind} M=300")
+    assert_close_rel(mod(x[:1]), ref[:1], 1e-3, f"{kind} M=1")
+    assert_close_rel(mod(x[:6]), ref[:6], 1e-3, f"{kind} M=6")
+
+
+def test_act_order_full_size_llama_layer():
+    """BASELINE configs[2]: desc_act=True (random g_idx) on a full-size Llama-3-8B projection, decode and prefill."""
+    K, N = 4096, 4096
+    L = make_layer(K, N, bits=4, group_size=128, sym=True, desc_act=True, seed=77)
+    mod = _module(L)
+    assert mod.perm is not None
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.randn(257, K, generator=gen) * 0.5).to(torch.float16)
+    ref = oracle_forward(L, x)
+    assert_close_rel(mod(x.to(DEV)), ref, 1e-3, "act-order M=257")
+    assert_close_rel(mod(x[:1].to(DEV)), ref[:1], 1e-3, "act-order M=1")
+    assert_close_rel(mod(x[:8].to(DEV)), ref[:8], 1e-3, "act-order M=8")
