@@ -199,6 +199,25 @@ int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t*
   MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
                        workspace_bytes, stream);
   if (decode_supported(a)) return check_cuda(launch_decode(a), "b2q_mm(decode)");
+  // small batches (9 <= M <= 16): two passes of the decode tier over blocks of 8 rows beat the single-CTA tcgen05 tier,
+  // whose grid of N/128 CTAs cannot fill 148 SMs (measured 28 us for 4096x4096 at any M <= 128 against 16.6 us here;
+  // at M = 32 the two are equal); the weights of the second pass come from L2.  A swapped-operand tcgen05 tier with
+  // cluster split-K is the planned replacement for 9 <= M <= 128.
+  {
+    MmArgs a8 = a;
+    a8.M = 8;
+    if (M > 8 && M <= 16 && decode_supported(a8) && perm == nullptr) {
+      for (int m0 = 0; m0 < M; m0 += 8) {
+        MmArgs ab = a;
+        ab.M = (M - m0 < 8) ? (M - m0) : 8;
+        ab.x = static_cast<const char*>(x) + (size_t)m0 * K * 2;
+        ab.out = static_cast<char*>(out) + (size_t)m0 * N * 2;
+        int e = check_cuda(launch_decode(ab), "b2q_mm(decode x blocks)");
+        if (e != 0) return e;
+      }
+      return 0;
+    }
+  }
   if (M == 1 && bits == 8 && K % 128 == 0) return check_cuda(launch_gemv(a), "b2q_mm(gemv)");
   {
     const char* e = getenv("B2Q_GEMM_1CTA");

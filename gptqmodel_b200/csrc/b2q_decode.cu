@@ -51,7 +51,7 @@ __device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&d)[4], const ui
 // (UBLKCP) and tracked by one mbarrier per stage: up to DEC_STAGES * 2 KB per warp are in flight with no register
 // cost, which is what keeps > 100 KB per SM outstanding (the first, register-prefetch version of this kernel kept
 // 2 KB per warp in flight and topped out at ~3 TB/s incremental: profiles/r01_decode_notes.md).
-constexpr int DEC_STAGES = 4;
+constexpr int DEC_STAGES = 4;  // maximum ring depth; the launch picks 4 or 2 stages (`stl` = log2) to fit shared memory
 constexpr int DEC_QUAD_BYTES = 2048;
 
 template <bool ASYM, bool G64>
@@ -156,7 +156,8 @@ __device__ __forceinline__ TileRef<T> resolve_tile(const DecSets& S, int gt) {
 template <typename T, bool ASYM, bool G64>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     decode_kernel(const __grid_constant__ DecSets S, const int32_t* __restrict__ perm, const T* __restrict__ x, int M,
-                  int K, int gsh, int qpc, int max_tiles, int ngroups, unsigned long long* __restrict__ trace) {
+                  int K, int gsh, int qpc, int max_tiles, int ngroups, int stl,
+                  unsigned long long* __restrict__ trace) {
   using E = ET<T>;
   extern __shared__ __align__(128) uint8_t dsm[];
   // optional phase timestamps (debug): trace[blockIdx.x * 16 + slot] = %globaltimer (ns)
@@ -185,8 +186,9 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const int q0 = blockIdx.y * qpc;
   const int q1 = min(q0 + qpc, nquads);
   const int kspan = qpc * 128;
-  uint8_t* ring = dsm + (size_t)warp * DEC_STAGES * DEC_QUAD_BYTES;
-  T* sx = reinterpret_cast<T*>(dsm + (size_t)nwarps * DEC_STAGES * DEC_QUAD_BYTES);
+  const int nst = 1 << stl;  // ring stages per warp (2 or 4)
+  uint8_t* ring = dsm + (size_t)warp * nst * DEC_QUAD_BYTES;
+  T* sx = reinterpret_cast<T*>(dsm + (size_t)nwarps * nst * DEC_QUAD_BYTES);
   float* xsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sx) + (size_t)M * kspan * sizeof(T));
   float* red = xsum + qpc * 2 * 8;
   float* part = red + 2 * nwarps * 256;  // [ngroups][max_tiles][256]
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     if (U > 0) iss_begin_tile();
 #pragma unroll
     for (int i = 0; i < DEC_STAGES; ++i)
-      if (iss_u < U) iss_one(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i);
+      if (i < nst && iss_u < U) iss_one(smem_u32(ring) + i * DEC_QUAD_BYTES, bars + 8 * i);
   }
   // scale / zero prefetch cursor (all lanes): this lane's 4 feature rows are +0, +8, +16, +24 from sc_next
   const int gstep = (2 * gw) >> gsh;           // quantisation groups between consecutive quads of this warp
@@ -342,8 +344,8 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     for (int qi = 0; qi < nq; ++qi, ++u, xf_a += xf_qstep, xs_a += xs_qstep) {
       DScale<ASYM, G64> nxt;
       if (u + 1 < U) fetch_scales(nxt);
-      const int st = u & (DEC_STAGES - 1);
-      mbar_wait(bars + 8 * st, (uint32_t)(u / DEC_STAGES) & 1u);
+      const int st = u & (nst - 1);
+      mbar_wait(bars + 8 * st, (uint32_t)(u >> stl) & 1u);
       const uint32_t wq_a = ring_a + st * DEC_QUAD_BYTES;
       float dd[2][2][4];  // [kbl][ftl][c]: four independent mma accumulator chains
 #pragma unroll
@@ -473,12 +475,12 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
 void* g_trace_ptr = nullptr;
 
 struct DecodeCfg {
-  int C, ks, warps, qpc, max_tiles, ngroups;
+  int C, ks, warps, qpc, max_tiles, ngroups, stl;
   size_t smem;
 };
 
-static size_t decode_smem(int M, int warps, int qpc, int max_tiles) {
-  return (size_t)warps * DEC_STAGES * DEC_QUAD_BYTES + (size_t)M * qpc * 128 * 2 + (size_t)qpc * 2 * 8 * 4 +
+static size_t decode_smem(int M, int warps, int qpc, int max_tiles, int nst) {
+  return (size_t)warps * nst * DEC_QUAD_BYTES + (size_t)M * qpc * 128 * 2 + (size_t)qpc * 2 * 8 * 4 +
          (size_t)2 * warps * 256 * 4 + (size_t)max_tiles * 256 * 4 + (size_t)warps * DEC_STAGES * 8 + 16;
 }
 
@@ -504,7 +506,13 @@ static bool decode_config(const MmArgs& a, int NT, DecodeCfg& best) {
       if (C * ngroups > NT) C = (NT + ngroups - 1) / ngroups;
       if (C < 1) C = 1;
       const int max_tiles = (NT + C * ngroups - 1) / (C * ngroups);  // per group
-      const size_t smem = decode_smem(a.M, warps, qpc, ks > 1 ? max_tiles * ngroups : 0);
+      // ring depth 4 when it fits, else 2 (measured: no loss at 2 stages, profiles/r01_decode_notes.md)
+      int stl = 2;
+      size_t smem = decode_smem(a.M, warps, qpc, ks > 1 ? max_tiles * ngroups : 0, 4);
+      if (smem > 200 * 1024) {
+        stl = 1;
+        smem = decode_smem(a.M, warps, qpc, ks > 1 ? max_tiles * ngroups : 0, 2);
+      }
       if (smem > 200 * 1024) continue;
       const int qpw = (qpc + gwarps - 1) / gwarps;  // quads per warp per tile
       // calibrated on the B200 sweep (profiles/r01_decode_notes.md): per tile = quads/warp + barrier epilogue,
@@ -513,7 +521,7 @@ static bool decode_config(const MmArgs& a, int NT, DecodeCfg& best) {
           (double)max_tiles * (qpw + 0.35) / ngroups + (ks > 1 ? 0.6 : 0.0) + (16 - warps) * 0.04 * max_tiles * qpw;
       if (cost < best_cost) {
         best_cost = cost;
-        best = DecodeCfg{C, ks, warps, qpc, ks > 1 ? max_tiles : 0, ngroups, smem};
+        best = DecodeCfg{C, ks, warps, qpc, ks > 1 ? max_tiles : 0, ngroups, stl, smem};
         found = true;
       }
     }
@@ -546,7 +554,7 @@ static int launch_decode_t(const MmArgs& a, const DecSets& sets, const DecodeCfg
   if (a.group_size == 64) gsh = 0;
   else if (a.group_size == 128) gsh = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sets, a.perm, (const T*)a.x, a.M, a.K, gsh, c.qpc, c.max_tiles,
-                                     c.ngroups, (unsigned long long*)g_trace_ptr);
+                                     c.ngroups, c.stl, (unsigned long long*)g_trace_ptr);
   return (int)e;
 }
 

@@ -146,7 +146,7 @@ def test_forward_matches_oracle_fp16(K, N, bits, gs, sym, desc, bias):
     L = make_layer(K, N, bits=bits, group_size=gs, sym=sym, desc_act=desc, bias=bias, seed=42)
     mod = _module(L)
     gen = torch.Generator().manual_seed(43)
-    for M in (1, 2, 7, 64, 128, 129, 300):
+    for M in (1, 2, 7, 12, 20, 32, 64, 128, 129, 300):
         x = (torch.randn(M, K, generator=gen) * 0.5).to(torch.float16)
         ref = oracle_forward(L, x)
         out = mod(x.to(DEV))
