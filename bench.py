@@ -148,22 +148,32 @@ def build_stack(device, rank, world, layers, fuse=True):
     return stack
 
 
-def run_stack(stack, h, world):
-    """One pass of the hot path over a batch h [M, hidden]; returns the last hidden state."""
+P2P_AR = None  # optional gptqmodel_b200.tp.P2PAllReduce (--p2p-allreduce): our one-shot kernel over NVLink peer memory
+
+
+def _all_reduce(t):
     import torch.distributed as dist
 
+    if P2P_AR is not None and t.numel() <= P2P_AR.max_elems:
+        P2P_AR(t)
+    else:
+        dist.all_reduce(t)
+
+
+def run_stack(stack, h, world):
+    """One pass of the hot path over a batch h [M, hidden]; returns the last hidden state."""
     for mods in stack:
         a = mods["q_proj"](h)
         mods["k_proj"](h)
         mods["v_proj"](h)
         h2 = mods["o_proj"](a)
         if world > 1:
-            dist.all_reduce(h2)
+            _all_reduce(h2)
         g = mods["gate_proj"](h2)
         mods["up_proj"](h2)
         h = mods["down_proj"](g)
         if world > 1:
-            dist.all_reduce(h)
+            _all_reduce(h)
     return h
 
 
@@ -300,6 +310,8 @@ def main():
     ap.add_argument("--prefill-iters", type=int, default=0, help="0 = auto")
     ap.add_argument("--layers", type=int, default=CFG["layers"], help="debug: fewer layers (result marked invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--p2p-allreduce", action="store_true",
+                    help="decode all-reduces through b2q_allreduce (one-shot kernel over NVLink peer memory) instead of NCCL")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinear (224/step) instead of fusing q/k/v and gate/up")
     args = ap.parse_args()
 
@@ -324,6 +336,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     peaks = load_peaks()
+    if world > 1 and args.p2p_allreduce:
+        from gptqmodel_b200 import tp as _tp
+
+        global P2P_AR
+        P2P_AR = _tp.P2PAllReduce(device, max_elems=8 * CFG["hidden"])
 
     stack = build_stack(device, rank, world, args.layers, fuse=not args.no_fuse)
     hidden = CFG["hidden"]
@@ -411,7 +428,9 @@ def main():
             "config": {
                 "workload": f"{CFG['name']} int4 g128 sym QuantLinear stack ({n_lin} linears): bs=1 decode step "
                             f"(value) + {Mp}-token prefill pass (prefill.*)",
-                "parallelism": f"tp{world}",
+                "parallelism": f"tp{world}" + ("" if world == 1 else
+                                               (", decode all-reduce: b2q_allreduce (P2P one-shot kernel)"
+                                                if args.p2p_allreduce else ", all-reduce: NCCL")),
                 "l2": "3.63 GB of distinct weights per step >> 126 MB L2: no flush needed between timed steps",
                 "timing": "CUDA graph of the whole step, CUDA events around K replays, max over ranks",
             },

@@ -111,6 +111,24 @@ int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K
   return check_cuda(launch_prepack(qweight, perm, packed, K, N, bits, (cudaStream_t)stream), "b2q_prepack");
 }
 
+int b2q_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs, size_t flag_offset,
+                  int max_elems, void* seq, void* stream) {
+  if (inout == nullptr || peer_bufs == nullptr || seq == nullptr || world < 1 || world > 8 || rank < 0 ||
+      rank >= world || n <= 0 || n % 8 != 0 || n > max_elems || (dtype != 0 && dtype != 1) ||
+      (reinterpret_cast<uintptr_t>(inout) & 15) || flag_offset % 16 != 0) {
+    set_error("b2q_allreduce: bad argument (n=%d max=%d rank=%d world=%d; n %% 8 == 0, 16-byte aligned, world <= 8)", n,
+              max_elems, rank, world);
+    return -2;
+  }
+  for (int i = 0; i < world; ++i)
+    if (peer_bufs[i] == nullptr) {
+      set_error("b2q_allreduce: peer buffer %d is NULL", i);
+      return -2;
+    }
+  return check_cuda(launch_allreduce(inout, n, dtype, rank, world, peer_bufs, flag_offset, max_elems, seq,
+                                     (cudaStream_t)stream), "b2q_allreduce");
+}
+
 int b2q_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, void* stream) {
   if (x == nullptr || perm == nullptr || out == nullptr || M < 0 || K <= 0) {
     set_error("b2q_permute_cols: bad argument");

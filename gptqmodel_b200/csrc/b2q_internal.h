@@ -35,6 +35,8 @@ int launch_decode_multi(const MmArgs& a, int nsets, const void* const* packed, c
 int launch_gemm(const MmArgs& a);
 int launch_gemm2(const MmArgs& a, const void* x);
 int gemm_gshc(const MmArgs& a);  // 4-bit, CTA-pair (cta_group::2) tier; x already permuted
+int launch_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs,
+                     size_t flag_offset, int max_elems, void* seq, cudaStream_t stream);
 void set_error(const char* fmt, ...);
 extern void* g_trace_ptr;  // debug: device buffer for phase timestamps of the decode kernel (nullptr = off)
 

@@ -95,6 +95,50 @@ def all_reduce_sum_(t: torch.Tensor, group: Optional[dist.ProcessGroup] = None) 
     return t
 
 
+class P2PAllReduce:
+    """One-shot all-reduce(sum) of small 16-bit tensors over NVLink peer memory (`b2q_allreduce`), CUDA-graph safe.
+
+    PyTorch's symmetric-memory rendezvous is used only to allocate the buffer and map the peers' pointers; the
+    collective itself is our kernel (gptqmodel_b200/csrc/b2q_allreduce.cu).  Use for the row-parallel QuantLinear
+    output at decode time (8-16 KB); large prefill tensors stay on NCCL.
+    """
+
+    def __init__(self, device, max_elems: int = 16384, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._lib import lib
+
+        self._lib = lib
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise NotImplementedError("P2PAllReduce: at most 8 GPUs (one NVLink domain)")
+        self.max_elems = (max_elems + 7) // 8 * 8
+        self.flag_offset = 2 * self.world * self.max_elems * 2
+        nbytes = self.flag_offset + 2 * self.world * 4
+        nbytes = (nbytes + 1023) // 1024 * 1024
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        self._peers = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's buffer is zeroed before anybody pushes into it
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        from ._lib import check
+
+        n = t.numel()
+        if not t.is_contiguous() or n % 8 != 0 or n > self.max_elems or t.dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("P2PAllReduce: contiguous fp16/bf16 tensor with numel % 8 == 0 and <= max_elems expected")
+        check(self._lib.b2q_allreduce(t.data_ptr(), n, 0 if t.dtype == torch.float16 else 1, self.rank, self.world,
+                                      self._peers, self.flag_offset, self.max_elems, self.seq.data_ptr(),
+                                      torch.cuda.current_stream(t.device).cuda_stream), "b2q_allreduce")
+        return t
+
+
 class RowParallelLinear(torch.nn.Module):
     """Wraps a row-sharded QuantLinear: forward(x_shard) -> all-reduced full output."""
 

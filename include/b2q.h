@@ -83,6 +83,15 @@ int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const 
                      const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* N, int M, int K,
                      int bits, int group_size, int dtype, void* stream);
 
+/* In-place all-reduce(sum) of a small 16-bit vector (n % 8 == 0, n <= max_elems) across `world` <= 8 GPUs of one
+ * NVLink domain: the single collective of a row-parallel QuantLinear at decode time (the reference has
+ * none).  peer_bufs is a HOST array of `world` device pointers to every rank's symmetric buffer (this rank's included),
+ * each laid out as data[2][world][max_elems] (16-bit) followed at byte `flag_offset` by flags[2][world] (u32),
+ * zero-initialised once; `seq` is a device u32 counter owned by this rank, zero-initialised once.  Every rank must
+ * issue the same sequence of calls.  One CTA pushes, flags, waits and sums over peer memory; no NCCL. */
+int b2q_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs, size_t flag_offset,
+                  int max_elems, void* seq, void* stream);
+
 /* Debug: device buffer (>= 148*16 uint64) receiving %globaltimer phase stamps of the decode kernel; NULL = off. */
 void b2q_debug_set_trace(void* device_buffer);
 

@@ -22,6 +22,18 @@ x = (torch.randn(1, 1024, device=dev) * 0.5).to(torch.float16)
 def step():
     h = md(mu(x)); dist.all_reduce(h); return h
 P("eager step"); y = step(); torch.cuda.synchronize(); P("eager ok", float(y.float().abs().mean()))
+P("P2PAllReduce init")
+ar = tp.P2PAllReduce(dev, max_elems=8192)
+P("peers", [hex(int(p)) for p in ar.hdl.buffer_ptrs])
+for it in range(5):
+    v = ((torch.arange(4096, device=dev) % 17).float() * 0.01 * (rank + 1) + it).to(torch.float16)
+    ref = v.clone(); dist.all_reduce(ref)
+    got = ar(v.clone()); torch.cuda.synchronize()
+    P("p2p allreduce", it, "max diff", float((got.float() - ref.float()).abs().max()))
+nccl_step = step
+def step():
+    h = md(mu(x)); ar(h); return h
+y2 = step(); torch.cuda.synchronize(); P("p2p step vs nccl step", float((y2.float() - y.float()).abs().max()))
 s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
 with torch.cuda.stream(s):
     for _ in range(2): step()
@@ -32,4 +44,13 @@ with torch.cuda.graph(g):
 P("captured; replay")
 for _ in range(3): g.replay()
 torch.cuda.synchronize(); P("replay ok", float(y.float().abs().mean()))
+import time as _t
+for name, fn in (("p2p", step), ("nccl", nccl_step)):
+    gg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gg):
+        for _ in range(50): fn()
+    gg.replay(); torch.cuda.synchronize(); t0 = _t.perf_counter()
+    for _ in range(20): gg.replay()
+    torch.cuda.synchronize(); P(name, "us per (2 linears + allreduce):", (_t.perf_counter() - t0) / 20 / 50 * 1e6)
+    del gg
 del g; torch.cuda.synchronize(); dist.barrier(); P("done"); os._exit(0)
