@@ -1,19 +1,16 @@
-// b2q_gemv.cu — batch-1 decode path: out[n] = sum_k x[k] * s[g(k), n] * (q[k, n] - z[g(k), n])  (+ bias).
+// b2q_gemv.cu — 8-bit, batch-1 decode path: out[n] = sum_k x[k] * s[g(k), n] * (q[k, n] - z[g(k), n])  (+ bias).
 //
-// HBM-bound (8,732,672 algorithmic bytes for 4096x4096 g128).  Design:
-//  * grid = (N/32 feature tiles) x (KS split-K CTAs), the KS CTAs of one feature tile form a thread-block
-//    cluster and reduce their partial sums through distributed shared memory (no atomics, no workspace,
-//    no output zeroing, deterministic).
-//  * each lane owns ONE output feature; a warp reads one B2Q tile row (32 features x 32 k = 512 B) per
-//    128-bit-per-lane coalesced request, 4 requests in flight per lane, issued BEFORE the activations are
-//    staged (weights do not depend on x).
-//  * the nibble -> fp16 conversion is one LOP3 per pair (1024+q, exact); the multiply-accumulate is the
-//    sm_100a mixed-precision FMA  fma.rn.f32.f16 (SASS FHFMA): exact fp16 x fp16 product, fp32 accumulate,
-//    no unpack/convert instructions.  The zero-point and the 1024 bias are removed once per group with
-//    pre-reduced activation sums:  sum (q-z) x = sum (1024+q) x - (1024+z) * sum x.
-//  * act-order: rows were sorted by group at prepack; the x gather x[perm[k']] is fused into the smem staging.
-// Replaces, for M == 1, the work of TorchLinear.forward (qlinear/torch.py:302-347) / the decode tiers of
-// swordfish_mm (swordfish_mm.cu:216-286) and Marlin (gptq_marlin.cu) in the reference.
+// CUDA-core tier on the T8 layout (uint4 T8[K/32][N/32][2][32], natural byte order).  (The 4-bit decode path started
+// as this kernel, was found issue-bound — profiles/r01_gemv_r1a.txt — and moved to b2q_decode.cu.)
+//  * grid = (N/32 feature tiles) x (KS split-K CTAs); the KS CTAs of one feature tile form a thread-block cluster
+//    and reduce their partial sums through distributed shared memory (no atomics, no workspace, deterministic);
+//  * each lane owns ONE output feature; a warp reads 32 features x 16 k per coalesced 512-byte request, 8 requests in
+//    flight per lane, issued BEFORE griddepcontrol.wait / the activation staging (weights do not depend on x);
+//  * PRMT builds exact 1024+q half pairs; the multiply-accumulate is the sm_100a mixed-precision FMA
+//    fma.rn.f32.f16 (SASS FHFMA): exact fp16 x fp16 product, fp32 accumulate.  The zero-point and the 1024 bias
+//    are removed once per group with pre-reduced activation sums: sum (q-z) x = sum (1024+q) x - (1024+z) sum x;
+//  * act-order: rows sorted by group at prepack; the x[perm[k']] gather is fused into the smem staging.
+// Replaces, for 8-bit M == 1, TorchLinear.forward (qlinear/torch.py:302-347) / Marlin's small-M path.
 #include "b2q_common.cuh"
 #include "b2q_internal.h"
 
@@ -67,25 +64,8 @@ template <typename T, int BITS>
 __device__ __forceinline__ void chunk_dot(const uint4* v, const uint4* __restrict__ xs, float& lo, float& hi) {
   using E = ET<T>;
   float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-  if (BITS == 4) {
-    const uint32_t w[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const uint4 xv = xs[t];  // x[8t .. 8t+7] as 4 packed pairs
-      uint32_t h[4];
-      E::unpack_w4(w[t], h);
-      a0 = E::fma_lo(h[0], xv.x, a0);
-      a1 = E::fma_hi(h[0], xv.x, a1);
-      b0 = E::fma_lo(h[1], xv.y, b0);
-      b1 = E::fma_hi(h[1], xv.y, b1);
-      a0 = E::fma_lo(h[2], xv.z, a0);
-      a1 = E::fma_hi(h[2], xv.z, a1);
-      b0 = E::fma_lo(h[3], xv.w, b0);
-      b1 = E::fma_hi(h[3], xv.w, b1);
-    }
-    lo += a0 + a1;
-    hi += b0 + b1;
-  } else {
+  static_assert(BITS == 8, "this tier handles the 8-bit T8 layout only");
+  {
     // 8-bit: natural byte order, 4 k per word; pair (k0,k1) = prmt(w, MAGIC8, 0x7150), (k2,k3) = 0x7352
     // fp16 only here (1024 + q, q < 256 fits the 10-bit mantissa); bf16 converts through fp32 instead.
 #pragma unroll
