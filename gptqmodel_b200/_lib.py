@@ -38,7 +38,7 @@ class B2QError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} not found: build it with `python -m gptqmodel_b200.build` "
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py` or `make -C gptqmodel_b200/csrc` "
             "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU/PyTorch fallback."
         )
     lib = ctypes.CDLL(LIB_PATH)
