@@ -60,26 +60,6 @@ struct DScale {
   uint32_t zw[(ASYM ? 1 : 0) * (G64 ? 2 : 1) + (ASYM ? 0 : 1)][4];
 };
 
-template <typename T, bool ASYM, bool G64>
-__device__ __forceinline__ void load_dscale(DScale<ASYM, G64>& q, const T* __restrict__ scales,
-                                            const uint32_t* __restrict__ qzeros, int quad, int gsh, int N, int nrow0) {
-  const int g0 = (quad * 2) >> gsh;  // group of k-block 2*quad   (gsh = log2(group_size / 64), 31 for per-channel)
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = nrow0 + (i >> 1) * 16 + (i & 1) * 8;
-    q.s[0][i] = *reinterpret_cast<const uint16_t*>(scales + (size_t)g0 * N + n);
-    if (ASYM) q.zw[0][i] = qzeros[(size_t)g0 * (N >> 3) + (n >> 3)];
-  }
-  if (G64) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = nrow0 + (i >> 1) * 16 + (i & 1) * 8;
-      q.s[G64 ? 1 : 0][i] = *reinterpret_cast<const uint16_t*>(scales + (size_t)(g0 + 1) * N + n);
-      if (ASYM) q.zw[G64 ? 1 : 0][i] = qzeros[(size_t)(g0 + 1) * (N >> 3) + (n >> 3)];
-    }
-  }
-}
-
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 r;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
@@ -101,12 +81,6 @@ __device__ __forceinline__ void issue_quad(uint32_t dst, uint32_t bar, const uin
 // Persistent-style CTA: blockIdx.x strides over the 32-feature tiles (tile = blockIdx.x + i * gridDim.x), blockIdx.y is
 // the split-K rank inside the cluster.  x is staged ONCE per CTA; the warps split the k-quads of every tile; each
 // warp's bulk-copy ring runs ahead across tile boundaries.
-__device__ __forceinline__ int ld_volatile_s32(const int* p) {
-  int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-
 // Up to DEC_MAX_SETS weight sets that consume the SAME activations (q/k/v, gate/up: "sibling" QuantLinears) are served
 // by one launch: the 32-feature tiles of all sets form one index space (tile_end = running totals).
 constexpr int DEC_MAX_SETS = 3;
@@ -193,8 +167,6 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   float* red = xsum + qpc * 2 * 8;
   float* part = red + 2 * nwarps * 256;  // [ngroups][max_tiles][256]
   const uint32_t bars = smem_u32(part + max_tiles * 256) + warp * DEC_STAGES * 8;
-  int* fin = reinterpret_cast<int*>(part + max_tiles * 256) + nwarps * DEC_STAGES * 2;  // fin[2] after the mbarriers
-  if (threadIdx.x == 0) fin[0] = fin[1] = 0;
   const bool PERM = perm != nullptr;
 
   // ---- 1. the first DEC_STAGES quads of this warp requested before anything else -----------------
