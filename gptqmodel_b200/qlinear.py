@@ -36,6 +36,11 @@ class SiblingGroup:
     outputs; each sibling's `forward(x)` then just picks its result up.  Every module keeps the reference's
     per-module `forward(x) -> y` contract (results are bit-identical to separate calls); only the launch count
     changes.  This is SURVEY.md §8 row f1 ("fused neighbours of the GEMM").
+
+    Contract: parked outputs are keyed on (data_ptr, version, M, dtype) of the activations, are handed out once, and
+    are dropped as soon as any member is called with different activations.  Under `torch.inference_mode()` tensors
+    carry no version counter, so a sibling must not be called with NEW contents in the SAME buffer unless the member
+    that launched (the first one called, q_proj / gate_proj in HF decoder layers) ran on those contents first.
     """
 
     def __init__(self, members):
