@@ -26,7 +26,10 @@ SYMBOLS = {
     "b2q_gemv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2q_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b2q_allreduce": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
+    "b2q_decode_allreduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
+    "b2q_decode_allreduce_flag_bytes": (_sz, []),
     "b2q_debug_set_trace": (None, [_vp]),
+    "b2q_debug_decode_plan": (_i, [_i, _i, _i, _i, _i, _i, _vp]),
     "b2q_permute_cols": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
 }
 

@@ -89,6 +89,27 @@ int b2q_version(void) { return B2Q_ABI_VERSION; }
 
 void b2q_debug_set_trace(void* device_buffer) { g_trace_ptr = device_buffer; }
 
+int b2q_debug_decode_plan(int version, int M, int K, int N, int ks, int warps, int* out8) {
+  if (out8 == nullptr || (version != 1 && version != 2) || M < 1 || M > 8 || K < 128 || K % 128 != 0 || N < 32 ||
+      N % 32 != 0) {
+    set_error("b2q_debug_decode_plan: bad argument (version=%d M=%d K=%d N=%d)", version, M, K, N);
+    return -2;
+  }
+  MmArgs a = {};
+  a.M = M;
+  a.K = K;
+  a.N = N;
+  a.bits = 4;
+  a.group_size = 128;
+  a.tune_ks = ks;
+  a.tune_warps = warps;
+  if (!decode_plan(version, a, N / 32, out8)) {
+    set_error("b2q_debug_decode_plan: no configuration fits shared memory (version=%d M=%d K=%d N=%d)", version, M, K, N);
+    return -1;
+  }
+  return 0;
+}
+
 const char* b2q_last_error(void) { return g_err; }
 
 size_t b2q_packed_bytes(int K, int N, int bits) { return (size_t)K * (size_t)N * (size_t)bits / 8; }
@@ -128,6 +149,45 @@ int b2q_allreduce(void* inout, int n, int dtype, int rank, int world, const void
   return check_cuda(launch_allreduce(inout, n, dtype, rank, world, peer_bufs, flag_offset, max_elems, seq,
                                      (cudaStream_t)stream), "b2q_allreduce");
 }
+
+int b2q_decode_allreduce(const void* x, const void* packed, const void* scales, const int32_t* qzeros,
+                         const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype,
+                         int rank, int world, const void* const* peer_bufs, size_t flag_offset, int max_elems,
+                         void* ctl, void* stream) {
+  int v = validate("b2q_decode_allreduce", x, packed, scales, out, M, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (peer_bufs == nullptr || ctl == nullptr || world < 2 || world > 8 || rank < 0 || rank >= world || max_elems <= 0 ||
+      (size_t)M * (size_t)N > (size_t)max_elems || flag_offset % 16 != 0 ||
+      flag_offset < (size_t)2 * world * (size_t)max_elems * sizeof(float)) {
+    set_error("b2q_decode_allreduce: bad argument (rank=%d world=%d M*N=%lld max_elems=%d flag_offset=%zu; 2 <= world <= 8, "
+              "M*N <= max_elems, flag_offset >= 2*world*max_elems*4 and a multiple of 16)",
+              rank, world, (long long)M * N, max_elems, flag_offset);
+    return -2;
+  }
+  DecodeAR ar = {};
+  ar.world = world;
+  ar.rank = rank;
+  ar.max_elems = max_elems;
+  ar.flag_offset = flag_offset;
+  ar.ctl = (uint32_t*)ctl;
+  for (int i = 0; i < world; ++i) {
+    if (peer_bufs[i] == nullptr) {
+      set_error("b2q_decode_allreduce: peer buffer %d is NULL", i);
+      return -2;
+    }
+    ar.buf[i] = const_cast<void*>(peer_bufs[i]);
+  }
+  MmArgs a = make_args(x, packed, scales, qzeros, nullptr, bias, out, M, K, N, bits, group_size, dtype, nullptr, 0,
+                       stream);
+  if (!decode_supported(a)) {
+    set_error("b2q_decode_allreduce: needs bits=4, 1 <= M <= 8, K %% 128 == 0, group_size 64|128|K (got bits=%d M=%d K=%d "
+              "g=%d)", bits, M, K, group_size);
+    return -2;
+  }
+  return check_cuda(launch_decode_allreduce(a, ar), "b2q_decode_allreduce");
+}
+
+size_t b2q_decode_allreduce_flag_bytes(void) { return decode_allreduce_flag_bytes(); }
 
 int b2q_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, void* stream) {
   if (x == nullptr || perm == nullptr || out == nullptr || M < 0 || K <= 0) {

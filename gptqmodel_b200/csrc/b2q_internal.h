@@ -25,11 +25,23 @@ struct MmArgs {
   int pdl;         // 1: launch with programmatic stream serialization (default)
 };
 
+// Fused row-parallel all-reduce of the decode tier (b2q_decode2.cu).  world <= 1: plain decode.
+struct DecodeAR {
+  int world, rank;
+  int max_elems;       // f32 elements per (slot, rank) row of the symmetric buffer, >= M * N
+  size_t flag_offset;  // byte offset of the u32 flags[world][160] inside the symmetric buffer
+  void* buf[8];        // every rank's symmetric buffer (this rank's included), device / peer-mapped pointers
+  uint32_t* ctl;       // this rank's {seq, arrive} counters, zero-initialised once
+};
+int launch_decode_allreduce(const MmArgs& a, const DecodeAR& ar);
+size_t decode_allreduce_flag_bytes();
+
 int launch_prepack(const void* qweight, const int32_t* perm, void* out, int K, int N, int bits, cudaStream_t stream);
 int launch_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, cudaStream_t stream);
 int launch_gemv(const MmArgs& a);     // 8-bit, M == 1: CUDA-core FHFMA GEMV
 int launch_decode(const MmArgs& a);   // 4-bit, M <= 8: mma.sync decode tier
 bool decode_supported(const MmArgs& a);
+bool decode_plan(int version, const MmArgs& a, int NT, int* out8);  // launch plan of the decode tier (host only)
 int launch_decode_multi(const MmArgs& a, int nsets, const void* const* packed, const void* const* scales,
                         const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* Ns);
 int launch_gemm(const MmArgs& a);

@@ -350,6 +350,31 @@ class B200QuantLinear(nn.Module):
             out = self.adapter.apply(x=x, out=out)
         return out
 
+    def forward_allreduce(self, x: torch.Tensor, ar) -> torch.Tensor:
+        """Row-parallel shard + all-reduce(sum) across the TP group in ONE launch (`b2q_decode_allreduce`).
+
+        `ar` is a `gptqmodel_b200.tp.FusedDecodeAllReduce`; decode tier only (4-bit, <= 8 tokens, no act-order).
+        EXPERIMENTAL in round 1 (compiled, not yet validated on GPUs)."""
+        if not self._prepacked:
+            raise B2QError("B200QuantLinear.forward_allreduce() before post_init()")
+        K, N = self.in_features, self.out_features
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        if not (1 <= M <= DECODE_MAX_M) or self.bits != 4 or self.perm is not None or x.dtype not in _DTYPE_CODE:
+            raise B2QError("forward_allreduce: decode tier only (bits=4, 1 <= tokens <= 8, no act-order, fp16/bf16)")
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+        check(
+            lib.b2q_decode_allreduce(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)),
+                                     _ptr(self._zeros_dev), _ptr(self._bias_for(x.dtype)), _ptr(out), M, K, N,
+                                     self.bits, self.group_size, _DTYPE_CODE[x.dtype], ar.rank, ar.world, ar._peers,
+                                     ar.flag_offset, ar.max_elems, ar.ctl.data_ptr(),
+                                     torch.cuda.current_stream(x.device).cuda_stream),
+            "b2q_decode_allreduce",
+        )
+        return out.reshape(x.shape[:-1] + (N,))
+
     # ---- helpers for tests / tools -------------------------------------------------------------------
     @classmethod
     def from_checkpoint_tensors(cls, qweight, qzeros, scales, g_idx, bits, group_size, bias=None, desc_act=None,

@@ -139,13 +139,57 @@ class P2PAllReduce:
         return t
 
 
-class RowParallelLinear(torch.nn.Module):
-    """Wraps a row-sharded QuantLinear: forward(x_shard) -> all-reduced full output."""
+class FusedDecodeAllReduce:
+    """Symmetric buffers for `b2q_decode_allreduce`: the row-parallel QuantLinear and its all-reduce in ONE kernel.
 
-    def __init__(self, inner: torch.nn.Module, group: Optional[dist.ProcessGroup] = None):
+    One instance per TP group and device serves every row-parallel layer (calls are stream-ordered); layout per rank:
+    f32 data[2][world][max_elems] | u32 flags (b2q_decode_allreduce_flag_bytes()), zero-initialised once.
+    EXPERIMENTAL in round 1 (compiled, not yet validated on GPUs).
+    """
+
+    def __init__(self, device, max_elems: int = 8 * 8192, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._lib import lib
+
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if not 2 <= self.world <= 8:
+            raise NotImplementedError("FusedDecodeAllReduce: 2..8 GPUs of one NVLink domain")
+        self.max_elems = (max_elems + 31) // 32 * 32
+        self.flag_offset = 2 * self.world * self.max_elems * 4
+        nbytes = self.flag_offset + int(lib.b2q_decode_allreduce_flag_bytes())
+        nbytes = (nbytes + 1023) // 1024 * 1024
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        self._peers = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.ctl = torch.zeros(2, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's buffer is zeroed before anybody pushes into it
+
+
+class RowParallelLinear(torch.nn.Module):
+    """Wraps a row-sharded QuantLinear: forward(x_shard) -> all-reduced full output.
+
+    reduce: None -> NCCL all-reduce; a `P2PAllReduce` -> our one-shot kernel after the matmul (decode-sized outputs);
+    a `FusedDecodeAllReduce` -> matmul and all-reduce in one launch when the input has <= 8 tokens.
+    """
+
+    def __init__(self, inner: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, reduce=None):
         super().__init__()
         self.inner = inner
         self.group = group
+        self.reduce = reduce
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return all_reduce_sum_(self.inner(x), self.group)
+        tokens = x.numel() // x.shape[-1]
+        if isinstance(self.reduce, FusedDecodeAllReduce) and 1 <= tokens <= 8 and getattr(self.inner, "perm", 1) is None \
+                and getattr(self.inner, "bits", 0) == 4:
+            return self.inner.forward_allreduce(x, self.reduce)
+        y = self.inner(x)
+        if isinstance(self.reduce, P2PAllReduce) and y.numel() <= self.reduce.max_elems and y.numel() % 8 == 0:
+            return self.reduce(y.contiguous())
+        return all_reduce_sum_(y, self.group)

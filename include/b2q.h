@@ -92,8 +92,32 @@ int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const 
 int b2q_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs, size_t flag_offset,
                   int max_elems, void* seq, void* stream);
 
+/* Row-parallel QuantLinear shard AND its all-reduce(sum) in ONE launch (decode tier: bits = 4, 1 <= M <= 8, no
+ * act-order; SURVEY.md §8e — the reference has no collective).  Every rank calls it with its K-shard (x [M, K/world],
+ * weights of those rows) and the same M, N; the kernel pushes its fp32 partial sums into every rank's symmetric buffer
+ * over NVLink peer memory, exchanges per-CTA flags, sums the `world` partials in rank order and stores
+ * out[M, N] = round(sum_r x_r @ dequant(W_r) (+ bias)) on every rank.  Pass the bias on ONE rank only
+ * (gptqmodel_b200.tp.shard_rows keeps it on rank 0).
+ *   peer_bufs   : HOST array of `world` device pointers to every rank's symmetric buffer (this rank's included), laid
+ *                 out as f32 data[2][world][max_elems], then at byte `flag_offset` (multiple of 16,
+ *                 >= 2*world*max_elems*4) u32 flags of b2q_decode_allreduce_flag_bytes() bytes; zero-initialised once
+ *   ctl         : this rank's device u32[2] {sequence, arrivals}, zero-initialised once
+ * Every rank must issue the same sequence of calls with the same shapes.  CUDA-graph safe (nothing is reset).
+ * EXPERIMENTAL in round 1: compiled, not yet validated on GPUs. */
+int b2q_decode_allreduce(const void* x, const void* packed, const void* scales, const int32_t* qzeros,
+                         const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype,
+                         int rank, int world, const void* const* peer_bufs, size_t flag_offset, int max_elems,
+                         void* ctl, void* stream);
+size_t b2q_decode_allreduce_flag_bytes(void);
+
 /* Debug: device buffer (>= 148*16 uint64) receiving %globaltimer phase stamps of the decode kernel; NULL = off. */
 void b2q_debug_set_trace(void* device_buffer);
+
+/* Debug / tests (host only, no GPU needed): the launch plan the decode tier would use for out[M, N] with N the total
+ * width of the (fused sibling) weight sets.  version 1 = b2q_decode.cu, 2 = the experimental b2q_decode2.cu.
+ * out8 = {CTA columns, split-K ranks (cluster size), warps per CTA, warps per tile group, k-quads (128 k) per CTA,
+ * tiles (32 features) per group, ring stages, dynamic shared memory bytes}.  ks / warps <= 0 = heuristic. */
+int b2q_debug_decode_plan(int version, int M, int K, int N, int ks, int warps, int* out8);
 
 /* out[m, k'] = x[m, perm[k']] for 16-bit elements. */
 int b2q_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, void* stream);

@@ -89,3 +89,56 @@ def test_v1_to_v2_conversion():
     m.qzero_format(1)
     m.convert_gptq_v1_to_v2()
     assert m.qzero_format() == 2 and int(m.qzeros[0, 0]) == 0x88888888 - (1 << 32)
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_decode_launch_plan_invariants(version):
+    # host-side planner of the decode tier (b2q_decode.cu / b2q_decode2.cu): every plan must cover all 32-feature
+    # tiles and all k-quads, fit one CTA (or one cluster) per SM and stay inside the shared-memory budget
+    out = (ctypes.c_int * 8)()
+    shapes = [(4096, 4096), (4096, 1024), (4096, 6144), (4096, 14336), (4096, 28672), (14336, 4096), (8192, 8192),
+              (8192, 1280), (28672, 8192), (1024, 32), (128, 32), (256, 96), (11008, 4096), (4096, 32000)]
+    for K, N in shapes:
+        for M in range(1, 9):
+            for ks, warps in ((0, 0), (2, 0), (0, 8)):
+                rc = g.lib.b2q_debug_decode_plan(version, M, K, N, ks, warps, out)
+                if rc != 0:
+                    assert ks != 0 or warps != 0 or version == 2, (version, M, K, N)  # the v1 heuristic always finds one
+                    continue
+                C, pks, pw, gw, qpc, max_tiles, stages, smem = list(out)
+                quads, tiles = K // 128, N // 32
+                assert 1 <= C and C * pks <= 148 and pks in (1, 2, 4, 8) and pw in (4, 8, 16), list(out)
+                assert pw % gw == 0 and stages in (2, 4) and smem <= 200 * 1024, list(out)
+                assert qpc * pks >= quads and (pks - 1) * qpc < quads, list(out)  # every rank owns >= 1 quad
+                ngroups = pw // gw
+                if version == 2 or pks > 1:
+                    assert C * ngroups * max_tiles >= tiles, list(out)
+                if ks > 0:
+                    assert pks == ks
+                if warps > 0:
+                    assert pw == warps
+    assert g.lib.b2q_debug_decode_plan(3, 1, 4096, 4096, 0, 0, out) == -2
+    assert g.lib.b2q_debug_decode_plan(2, 9, 4096, 4096, 0, 0, out) == -2
+
+
+def test_decode_allreduce_argument_validation_without_gpu():
+    # the fused row-parallel decode + all-reduce entry point: every bad call is refused before any CUDA work
+    one = ctypes.c_void_p(16)
+    peers = (ctypes.c_void_p * 2)(16, 16)
+    fb = g.lib.b2q_decode_allreduce_flag_bytes()
+    assert fb == 8 * 160 * 4
+    ok_off = 2 * 2 * 4096 * 4
+
+    def call(M=1, K=256, N=4096, bits=4, world=2, rank=0, peer=peers, off=ok_off, max_elems=4096, ctl=one):
+        return g.lib.b2q_decode_allreduce(one, one, one, None, None, one, M, K, N, bits, 128, 0, rank, world, peer, off,
+                                          max_elems, ctl, None)
+
+    assert call(world=1) == -2 and b"world" in g.lib.b2q_last_error()
+    assert call(world=9) == -2
+    assert call(rank=2) == -2
+    assert call(M=2) == -2 and b"max_elems" in g.lib.b2q_last_error()       # M*N > max_elems
+    assert call(off=ok_off - 16) == -2                                        # flags would overlap the data rows
+    assert call(ctl=None) == -2
+    assert call(peer=(ctypes.c_void_p * 2)(16, None)) == -2 and b"peer buffer 1" in g.lib.b2q_last_error()
+    assert call(bits=8) == -2 and b"bits=4" in g.lib.b2q_last_error()
+    assert call(M=9, max_elems=9 * 4096, off=2 * 2 * 9 * 4096 * 4) == -2     # decode tier: <= 8 tokens
