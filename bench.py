@@ -151,6 +151,19 @@ def build_stack(device, rank, world, layers, fuse=True):
 P2P_AR = None  # optional gptqmodel_b200.tp.P2PAllReduce (--p2p-allreduce): our one-shot kernel over NVLink peer memory
 
 
+FUSED_AR = None  # optional gptqmodel_b200.tp.FusedDecodeAllReduce (--fused-allreduce, experimental): matmul + all-reduce in one launch
+
+
+def _row_parallel(mod, x, world):
+    """o_proj / down_proj: the shard's matmul followed by the all-reduce of the partial sums (world > 1)."""
+    if world > 1 and FUSED_AR is not None and x.shape[0] <= 8:
+        return mod.forward_allreduce(x, FUSED_AR)
+    y = mod(x)
+    if world > 1:
+        _all_reduce(y)
+    return y
+
+
 def _all_reduce(t):
     import torch.distributed as dist
 
@@ -166,14 +179,10 @@ def run_stack(stack, h, world):
         a = mods["q_proj"](h)
         mods["k_proj"](h)
         mods["v_proj"](h)
-        h2 = mods["o_proj"](a)
-        if world > 1:
-            _all_reduce(h2)
+        h2 = _row_parallel(mods["o_proj"], a, world)
         g = mods["gate_proj"](h2)
         mods["up_proj"](h2)
-        h = mods["down_proj"](g)
-        if world > 1:
-            _all_reduce(h)
+        h = _row_parallel(mods["down_proj"], g, world)
     return h
 
 
@@ -314,7 +323,13 @@ def main():
                     help="keep NCCL for the small decode all-reduces (default: b2q_allreduce, our one-shot kernel over "
                          "NVLink peer memory; measured 715 vs 605 tok/s at TP-4)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinear (224/step) instead of fusing q/k/v and gate/up")
+    ap.add_argument("--decode-v2", action="store_true",
+                    help="EXPERIMENTAL: decode tier v2 (b2q_decode2.cu; sets B2Q_DECODE_V2=1), result marked experimental")
+    ap.add_argument("--fused-allreduce", action="store_true",
+                    help="EXPERIMENTAL (N > 1): row-parallel matmul + all-reduce in one launch (b2q_decode_allreduce)")
     args = ap.parse_args()
+    if args.decode_v2:
+        os.environ["B2Q_DECODE_V2"] = "1"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -347,6 +362,12 @@ def main():
             if rank == 0:
                 print(f"[bench] P2PAllReduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             P2P_AR = None
+
+    if world > 1 and args.fused_allreduce:
+        from gptqmodel_b200 import tp as _tp
+
+        global FUSED_AR
+        FUSED_AR = _tp.FusedDecodeAllReduce(device, max_elems=8 * CFG["hidden"])
 
     stack = build_stack(device, rank, world, args.layers, fuse=not args.no_fuse)
     hidden = CFG["hidden"]
@@ -440,6 +461,9 @@ def main():
                                                 else ", all-reduce: NCCL")),
                 "l2": "3.63 GB of distinct weights per step >> 126 MB L2: no flush needed between timed steps",
                 "timing": "CUDA graph of the whole step, CUDA events around K replays, max over ranks",
+                **({"experimental": [f for f, on in (("decode-v2", args.decode_v2),
+                                                     ("fused-allreduce", FUSED_AR is not None)) if on]}
+                   if (args.decode_v2 or FUSED_AR is not None) else {}),
             },
             "roofline": {
                 "kernel": "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL); "
