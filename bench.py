@@ -327,9 +327,13 @@ def main():
                     help="EXPERIMENTAL: decode tier v2 (b2q_decode2.cu; sets B2Q_DECODE_V2=1), result marked experimental")
     ap.add_argument("--fused-allreduce", action="store_true",
                     help="EXPERIMENTAL (N > 1): row-parallel matmul + all-reduce in one launch (b2q_decode_allreduce)")
+    ap.add_argument("--gemm-streamk", action="store_true",
+                    help="EXPERIMENTAL: stream-K work split of the CTA-pair prefill tier (b2q_gemm2s.cu; sets B2Q_GEMM2_STREAMK=1)")
     args = ap.parse_args()
     if args.decode_v2:
         os.environ["B2Q_DECODE_V2"] = "1"
+    if args.gemm_streamk:
+        os.environ["B2Q_GEMM2_STREAMK"] = "1"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -461,9 +465,9 @@ def main():
                                                 else ", all-reduce: NCCL")),
                 "l2": "3.63 GB of distinct weights per step >> 126 MB L2: no flush needed between timed steps",
                 "timing": "CUDA graph of the whole step, CUDA events around K replays, max over ranks",
-                **({"experimental": [f for f, on in (("decode-v2", args.decode_v2),
+                **({"experimental": [f for f, on in (("decode-v2", args.decode_v2), ("gemm-streamk", args.gemm_streamk),
                                                      ("fused-allreduce", FUSED_AR is not None)) if on]}
-                   if (args.decode_v2 or FUSED_AR is not None) else {}),
+                   if (args.decode_v2 or args.gemm_streamk or FUSED_AR is not None) else {}),
             },
             "roofline": {
                 "kernel": "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL); "

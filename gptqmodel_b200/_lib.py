@@ -25,6 +25,9 @@ SYMBOLS = {
     "b2q_decode_multi": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b2q_gemv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2q_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "b2q_streamk_workspace_bytes": (_sz, []),
+    "b2q_gemm_streamk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "b2q_debug_gemm_plan": (_i, [_i, _i, _i, _i, _vp, _vp, _i]),
     "b2q_allreduce": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
     "b2q_decode_allreduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
     "b2q_decode_allreduce_flag_bytes": (_sz, []),

@@ -73,6 +73,7 @@ static MmArgs make_args(const void* x, const void* packed, const void* scales, c
   a.stream = (cudaStream_t)stream;
   a.tune_ks = 0;
   a.tune_warps = 0;
+  a.sk_ws = nullptr;
   {
     const char* e = getenv("B2Q_DISABLE_PDL");
     a.pdl = (e != nullptr && e[0] == '1') ? 0 : 1;
@@ -266,6 +267,32 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
     if (e != nullptr && e[0] == '1') a.tune_ks = -1;
   }
   return check_cuda(launch_gemm(a), "b2q_gemm");
+}
+
+size_t b2q_streamk_workspace_bytes(void) { return gemm2s_workspace_bytes(); }
+
+int b2q_gemm_streamk(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+                     const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype,
+                     void* workspace, size_t workspace_bytes, void* sk_workspace, void* stream) {
+  int v = validate("b2q_gemm_streamk", x, packed, scales, out, M, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (bits != 4 || M <= 128 || sk_workspace == nullptr || (reinterpret_cast<uintptr_t>(sk_workspace) & 15)) {
+    set_error("b2q_gemm_streamk: needs bits=4, M > 128 and a 16-byte aligned stream-K workspace (got bits=%d M=%d)", bits,
+              M);
+    return -2;
+  }
+  MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
+                       workspace_bytes, stream);
+  a.sk_ws = sk_workspace;
+  return check_cuda(launch_gemm(a), "b2q_gemm_streamk");
+}
+
+int b2q_debug_gemm_plan(int M, int K, int N, int pair, int* plan5, int* items, int max_items) {
+  if (plan5 == nullptr || items == nullptr || M < 1 || K < 64 || K % 64 != 0 || N < 32 || max_items < 0) {
+    set_error("b2q_debug_gemm_plan: bad argument");
+    return -2;
+  }
+  return gemm2s_debug_items(M, K, N, pair, plan5, items, max_items);
 }
 
 int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,

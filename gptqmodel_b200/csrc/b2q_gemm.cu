@@ -373,7 +373,8 @@ int launch_gemm(const MmArgs& a) {
     if (e != 0) return e;
     x = a.workspace;
   }
-  if (a.bits == 4 && a.M > 128 && a.tune_ks != -1) return launch_gemm2(a, x);  // CTA-pair tier (tune_ks -1: force 1-CTA)
+  if (a.bits == 4 && a.M > 128 && a.tune_ks != -1)  // CTA-pair tier (tune_ks -1: force 1-CTA)
+    return a.sk_ws != nullptr ? launch_gemm2s(a, x, a.sk_ws) : launch_gemm2(a, x);
   const bool asym = a.qzeros != nullptr;
   const bool big = a.M > 128;
 #define B2Q_GEMM_CASE(T, BITS, ST)                                                              \

@@ -15,6 +15,8 @@ There is no CPU / PyTorch fallback: every forward goes through libb2q.so (includ
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Optional, Tuple
 
@@ -105,6 +107,20 @@ def fuse_siblings(mods) -> bool:
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
+
+
+_SK_WORKSPACES = {}
+
+
+def _streamk_workspace(device, stream) -> torch.Tensor:
+    """One zero-filled stream-K workspace per (device, stream); owned by the library after the first use, never freed
+    (CUDA graphs may hold its address)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+    ws = _SK_WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.b2q_streamk_workspace_bytes()), dtype=torch.uint8, device=device)
+        _SK_WORKSPACES[key] = ws
+    return ws
 
 
 class B200QuantLinear(nn.Module):
@@ -338,6 +354,20 @@ class B200QuantLinear(nn.Module):
         if self.perm is not None and M > 1:
             ws_bytes = lib.b2q_workspace_bytes(M, K, N, 1)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        if M > 128 and self.bits == 4 and os.environ.get("B2Q_GEMM2_STREAMK") == "1":
+            # EXPERIMENTAL (round 1: compiled, not GPU-validated): stream-K work split of the CTA-pair prefill tier
+            stream = torch.cuda.current_stream(x.device)
+            check(
+                lib.b2q_gemm_streamk(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)),
+                                     _ptr(self._zeros_dev), _ptr(self.perm), _ptr(self._bias_for(x.dtype)), _ptr(out),
+                                     M, K, N, self.bits, self.group_size, _DTYPE_CODE[x.dtype], _ptr(ws), ws_bytes,
+                                     _ptr(_streamk_workspace(x.device, stream)), stream.cuda_stream),
+                "b2q_gemm_streamk",
+            )
+            out = out.reshape(out_shape)
+            if self.adapter:
+                out = self.adapter.apply(x=x, out=out)
+            return out
         check(
             lib.b2q_mm(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)), _ptr(self._zeros_dev),
                        _ptr(self.perm), _ptr(self._bias_for(x.dtype)), _ptr(out), M, K, N, self.bits,

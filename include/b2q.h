@@ -75,6 +75,21 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
              const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
              size_t workspace_bytes, void* stream);
 
+/* b2q_gemm with the STREAM-K work split of the CTA-pair tier (bits = 4, M > 128; b2q_gemm2s.cu): the last wave of
+ * 256 x 256 output tiles is cut into equal k-block streams so that all SM pairs finish together (128 tiles on 74 pairs
+ * otherwise run as 2 waves at 86 %).  sk_workspace: b2q_streamk_workspace_bytes() bytes of device memory, 16-byte
+ * aligned, ZERO-FILLED ONCE by the caller and afterwards owned by the library (it parks fp32 partial tiles there and
+ * re-arms its arrival counters itself); one workspace per stream.  Same results as b2q_gemm up to fp32 summation order.
+ * EXPERIMENTAL in round 1: compiled, not yet validated on GPUs.
+ * b2q_debug_gemm_plan (host only): plan5 = {tiles, pairs, k-blocks per tile, data-parallel tiles, stream-K tiles},
+ * items = (tile, kb0, kb1, role) of CTA pair `pair` in processing order; role 0 whole tile, 1 + 16 * partials-awaited
+ * owner of a split tile, 2 contributor; returns the item count, or -1 if it exceeds max_items. */
+size_t b2q_streamk_workspace_bytes(void);
+int b2q_gemm_streamk(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
+                     const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype,
+                     void* workspace, size_t workspace_bytes, void* sk_workspace, void* stream);
+int b2q_debug_gemm_plan(int M, int K, int N, int pair, int* plan5, int* items, int max_items);
+
 /* Sibling layers that consume the SAME activations (q/k/v, gate/up; module order in the reference:
  * gptqmodel/models/definitions/llama.py:17-27) in ONE decode launch: nsets <= 3 weight sets given as HOST arrays of
  * device pointers; all sets share M <= 8, K, bits = 4, group_size, dtype and symmetry (qzeros all NULL or all non-NULL),

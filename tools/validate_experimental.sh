@@ -1,0 +1,45 @@
+#!/bin/bash
+# Round-2 checklist for the three code paths that were written in round 1 AFTER the GPU budget ran out (they compile
+# for sm_100a, their host logic and index arithmetic are covered by CPU tests, but they have never run on a GPU).
+# Run each block as ONE gpurun call; every command is wrapped in `timeout` so a protocol bug cannot hang the box.
+#
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh decode'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh gemm'
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 600 -- 'bash tools/validate_experimental.sh tp 2'
+set -u
+mkdir -p gpurun_out
+case "${1:-decode}" in
+  decode)
+    # 1. parity: the whole GPU suite with every decode launch routed through b2q_decode2.cu
+    B2Q_DECODE_V2=1 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/v2_tests.log
+    # 1b. the LDG staging path (B2Q_DECODE2_XTMA=0) and forced warp groups
+    B2Q_DECODE_V2=1 B2Q_DECODE2_XTMA=0 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "decode or cases or sibling" 2>&1 | tail -5 | tee -a gpurun_out/v2_tests.log
+    for gw in 4 8; do
+      B2Q_DECODE_V2=1 B2Q_DECODE2_GW=$gw timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "decode or cases or sibling" 2>&1 | tail -3 | tee -a gpurun_out/v2_tests.log
+    done
+    # 2. A/B: v1 vs v2 on the Llama-3-8B stack (same box, back to back)
+    timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err
+    timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 > gpurun_out/bench_v2.json 2> gpurun_out/bench_v2.err
+    tail -c 600 gpurun_out/bench_v1.json; echo; tail -c 600 gpurun_out/bench_v2.json
+    ;;
+  gemm)
+    B2Q_GEMM2_STREAMK=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/sk_tests.log
+    timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_dp.json 2> gpurun_out/bench_dp.err
+    timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --gemm-streamk > gpurun_out/bench_sk.json 2> gpurun_out/bench_sk.err
+    python - <<'PY'
+import json
+for f in ("gpurun_out/bench_dp.json", "gpurun_out/bench_sk.json"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1]); print(f, d.get("prefill"))
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
+    ;;
+  tp)
+    N=${2:-2}
+    timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29517 \
+        tools/tp_fused_smoke.py 2>&1 | tail -60 | tee gpurun_out/tp_fused_smoke.log
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29518 \
+        bench.py --gpus "$N" --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 --fused-allreduce 2>&1 | tail -3 | tee gpurun_out/bench_tp_fused.log
+    ;;
+esac
