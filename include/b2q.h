@@ -93,7 +93,9 @@ int b2q_debug_gemm_plan(int M, int K, int N, int pair, int* plan5, int* items, i
 /* Sibling layers that consume the SAME activations (q/k/v, gate/up; module order in the reference:
  * gptqmodel/models/definitions/llama.py:17-27) in ONE decode launch: nsets <= 3 weight sets given as HOST arrays of
  * device pointers; all sets share M <= 8, K, bits = 4, group_size, dtype and symmetry (qzeros all NULL or all non-NULL),
- * no act-order.  out[i] is [M, N[i]].  Same arithmetic as nsets separate b2q_decode calls (bit-identical results). */
+ * no act-order.  out[i] is [M, N[i]].  Same arithmetic as nsets separate b2q_decode calls; results are bit-identical
+ * whenever the fused launch cuts K like the single launches would (see b2q_debug_decode_plan), else they differ only
+ * in the order the fp32 partial sums are added. */
 int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const void* const* scales,
                      const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* N, int M, int K,
                      int bits, int group_size, int dtype, void* stream);
