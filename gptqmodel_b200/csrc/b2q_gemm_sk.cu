@@ -1,18 +1,13 @@
-// b2q_gemm.cu — prefill / batched path: out[M, N] = x[M, K] @ dequant(W)[K, N] (+ bias) on tcgen05 tensor cores.
+// b2q_gemm_sk.cu — single-CTA tcgen05 tier with CLUSTER SPLIT-K for small token counts (M <= 128).  EXPERIMENTAL:
+// selected only with B2Q_GEMM_SPLITK=1 until it has passed the GPU parity suite.
 //
-// One CTA computes a (128*MT tokens) x (128 features) output tile, K in blocks of 64, with a STAGES-deep
-// mbarrier ring and warp-specialised roles:
-//   warp 0      producer : TMA (cp.async.bulk.tensor, SWIZZLE_128B) for the activation tile and cp.async.bulk
-//                          for the packed int4/int8 weight tile (contiguous 2 KB B2Q rows), one elected lane
-//   warp 1      MMA      : allocates TMEM, one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//                          (M=128, N=128, K=16) with the fp32 accumulators in TMEM, tcgen05.commit -> mbarriers
-//   warps 2..5  dequant  : LDS.128 packed weights -> exact (q - z) * s in fp16/bf16 (integer subtract first, one
-//                          rounding: identical operands to the reference's torch dequant, qlinear/__init__.py:
-//                          1001-1003) -> 16-byte swizzled K-major st.shared -> fence.proxy.async -> mbarrier;
-//                          afterwards the same warps run the epilogue: tcgen05.ld TMEM -> regs -> (+bias) ->
-//                          fp16/bf16 -> 64-byte-per-thread coalesced global stores.
-// In the reference this is TorchLinear's dequant + torch.matmul (qlinear/torch.py:326-343), Marlin's
-// mma.sync kernel (marlin_template.h) and Swordfish's CUTLASS-derived prefill tier (swordfish_prefill_*.cuh).
+// The plain single-CTA tier (b2q_gemm.cu) launches N/128 CTAs: 32 of 148 SMs for a 4096-wide layer, 28 us for
+// 4096 x 4096 at any M <= 128 although the layer's 8.7 MB stream from HBM in 1.3 us (profiles/r01_gemm_notes.md).  Here
+// `ks` CTAs of a thread-block cluster share one 128-feature tile: each runs the SAME warp-specialised pipeline (TMA
+// activations, bulk-copied packed weights, exact dequant warps, tcgen05.mma into TMEM) over its own 1/ks of the
+// k-blocks, parks its fp32 accumulator in its own shared memory, and after one cluster barrier every CTA reduces an
+// interleaved share of the token rows over distributed shared memory (no atomics, no workspace, deterministic).
+// 4096 x 4096: 32 tiles x ks = 4 -> 128 CTAs, 16 k-blocks each.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -24,11 +19,12 @@
 
 namespace b2q {
 
-template <typename T, int BITS, bool ASYM, int MT, int STAGES>
+template <typename T, int BITS, bool ASYM, int STAGES>
 __global__ void __launch_bounds__(G_THREADS, 1)
-    gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
+    gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
                 const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, const T* __restrict__ bias,
-                T* __restrict__ out, int M, int K, int N, int group_size, int gshc) {
+                T* __restrict__ out, int M, int K, int N, int group_size, int gshc, int kpc) {
+  constexpr int MT = 1;
   using C = GemmCfg<BITS, MT, STAGES>;
   using E = ET<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -48,7 +44,9 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   const int n0 = blockIdx.x * G_BN, m0 = blockIdx.y * (128 * MT);
   const int nt0 = n0 >> 5;
   const int ntiles = min(4, NT - nt0);
-  const int nkb = K / G_BK;
+  // split-K: cluster rank z owns k-blocks [kb0, kb1); i = kb - kb0 drives the stage / phase bookkeeping
+  const uint32_t nrank = cluster_nctarank(), crank = cluster_ctarank();
+  const int kb0 = (int)crank * kpc, kb1 = min(K / G_BK, kb0 + kpc);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
@@ -76,9 +74,9 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       const int FT = N >> 4, ft0 = n0 >> 4;
       const uint32_t pbytes4 = (uint32_t)min(8, FT - ft0) * 512u;
       const uint32_t pbytes8 = (uint32_t)ntiles * C::SUB * 512u;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int s = (kb - kb0) % STAGES;
+        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         // 4-bit: scale / zero rows of the block's group(s) travel with the packed codes (no LDG in the dequant warps)
         const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
@@ -110,9 +108,9 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = umma_idesc_f16(E::FMT, 128, G_BN);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int s = (kb - kb0) % STAGES;
+      const uint32_t ph = ((kb - kb0) / STAGES) & 1;
       mbar_wait(bar_full + 8 * s, ph);
       mbar_wait(bar_bready + 8 * s, ph);
       tc_fence_after();
@@ -123,11 +121,11 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint64_t adesc = umma_desc_k_sw128(sA + s * C::A_BYTES + mt * (128 * G_BK * 2));
-            umma_f16(tbase + mt * G_BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tbase + mt * G_BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
         }
         umma_commit(bar_empty + 8 * s);
-        if (kb == nkb - 1) umma_commit(bar_tfull);
+        if (kb == kb1 - 1) umma_commit(bar_tfull);
       }
       __syncwarp();
     }
@@ -145,9 +143,9 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       f[2] = f[0] + 64;
       f[3] = f[0] + 72;
       // this lane's 16 k of block kb lie in 32-k chunk 2*kb + (tt>>1); its scale / zero row was staged by the producer
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int s = (kb - kb0) % STAGES;
+        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
         mbar_wait(bar_full + 8 * s, ph);
         const uint8_t* pst = smem + (sP - smem_base) + s * C::P_BYTES;
         const uint4* pj = reinterpret_cast<const uint4*>(pst);
@@ -189,12 +187,12 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       const int nsafe = (n < N) ? n : 0;
       const int ntl = t >> 5;
       SZRaw cur[2], nxt[2];
-      cur[0] = load_sz<T, BITS, ASYM>(scales, qzeros, 0, nsafe, N);
-      cur[1] = load_sz<T, BITS, ASYM>(scales, qzeros, 1 >> gshc, nsafe, N);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        if (kb + 1 < nkb) {
+      cur[0] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb0) >> gshc, nsafe, N);
+      cur[1] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb0 + 1) >> gshc, nsafe, N);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int s = (kb - kb0) % STAGES;
+        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
+        if (kb + 1 < kb1) {
           nxt[0] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2) >> gshc, nsafe, N);
           nxt[1] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 3) >> gshc, nsafe, N);
         }
@@ -229,40 +227,63 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     }
 
     // ================================ epilogue ================================
+    // 1. this rank's fp32 accumulator -> its own shared memory (the pipeline buffers are idle once bar_tfull fired:
+    //    every TMA load was consumed by an MMA that has completed).  part[row][float4 chunk ^ (row & 31)]
     mbar_wait(bar_tfull, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int row = m0 + mt * 128 + q * 32 + lane;
+    {
+      const int prow = q * 32 + lane;
 #pragma unroll
       for (int cc = 0; cc < G_BN / 32; ++cc) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tbase + ((uint32_t)(q * 32) << 16) + mt * G_BN + cc * 32, r);
+        tmem_ld_32x32b_x32(tbase + ((uint32_t)(q * 32) << 16) + cc * 32, r);
         tmem_ld_wait();
-        const int nc = n0 + cc * 32;
-        if (row < M && nc < N) {
-          T* dst = out + (size_t)row * N + nc;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              // reference order: round the matmul to the output dtype, then add bias (torch.py:337-342)
-              float f0 = __uint_as_float(r[v * 8 + 2 * i]), f1 = __uint_as_float(r[v * 8 + 2 * i + 1]);
-              if (bias != nullptr) {
-                f0 = E::to_f(E::from_f(f0)) + E::to_f(bias[nc + v * 8 + 2 * i]);
-                f1 = E::to_f(E::from_f(f1)) + E::to_f(bias[nc + v * 8 + 2 * i + 1]);
-              }
-              pk[i] = E::pack2(f0, f1);
-            }
-            *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+        for (int v = 0; v < 8; ++v) {
+          const uint32_t chunk = (uint32_t)(cc * 8 + v) ^ (uint32_t)(prow & 31);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sA + (uint32_t)prow * 512u + chunk * 16u),
+                       "r"(r[4 * v]), "r"(r[4 * v + 1]), "r"(r[4 * v + 2]), "r"(r[4 * v + 3])
+                       : "memory");
         }
       }
     }
     tc_fence_before();
   }
+  // 2. all ranks' partials are in place (cluster barrier = CTA barrier + cross-CTA release/acquire)
+  cluster_sync_all();
+  if (warp >= 2) {
+    // 3. rank z reduces token rows z, z + nrank, ... over all ranks through distributed shared memory
+    const int t = threadIdx.x - 64;  // 0..127
+    const int chunk = t & 31;        // float4 chunk (4 features) inside the 128-feature tile
+    const int nc = n0 + chunk * 4;
+    for (int rl = (int)crank + (int)nrank * (t >> 5); rl < 128; rl += (int)nrank * 4) {
+      const int row = m0 + rl;
+      if (row >= M || nc >= N) continue;
+      const uint32_t local = sA + (uint32_t)rl * 512u + (((uint32_t)chunk ^ (uint32_t)(rl & 31)) << 4);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (uint32_t r = 0; r < nrank; ++r) {
+        uint32_t ra;
+        float4 v;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(r));
+        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(ra)
+                     : "memory");
+        acc[0] += v.x;
+        acc[1] += v.y;
+        acc[2] += v.z;
+        acc[3] += v.w;
+      }
+      if (bias != nullptr) {
+        // reference order: round the matmul to the output dtype, then add bias (torch.py:337-342)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = E::to_f(E::from_f(acc[i])) + E::to_f(bias[nc + i]);
+      }
+      *reinterpret_cast<uint2*>(out + (size_t)row * N + nc) = make_uint2(E::pack2(acc[0], acc[1]), E::pack2(acc[2], acc[3]));
+    }
+  }
+  cluster_sync_all();  // keep every rank's shared memory alive until all peers have read it
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -270,110 +291,64 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
+int make_x_tmap(CUtensorMap* map, const void* x, int M, int K, int dtype);  // b2q_gemm.cu
+
+// split-K ranks for an M <= 128 launch: fill ~148 SMs, keep >= 4 k-blocks per rank; 1 = not worth it
+int gemm_sk_ranks(int K, int N) {
+  const int tiles = (N + G_BN - 1) / G_BN, nkb = K / G_BK;
+  int ks = 1;
+  while (ks < 8 && tiles * ks * 2 <= 148 && nkb / (ks * 2) >= 4) ks *= 2;
+  return ks;
 }
 
-int make_x_tmap(CUtensorMap* map, const void* x, int M, int K, int dtype) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (enc == nullptr) {
-    set_error("b2q_gemm: cuTensorMapEncodeTiled not available from the driver");
-    return -1;
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
-  cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)G_BK, 128};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("b2q_gemm: cuTensorMapEncodeTiled failed (%d) for x=%p M=%d K=%d", (int)r, x, M, K);
-    return -1;
-  }
-  return 0;
-}
-
-// log2(32-k chunks per group); 31 for per-channel (every chunk maps to group 0)
-int gemm_gshc(const MmArgs& a) {
-  if (a.group_size == 32) return 0;
-  if (a.group_size == 64) return 1;
-  if (a.group_size == 128) return 2;
-  return 31;
-}
-
-template <typename T, int BITS, bool ASYM, int MT, int STAGES>
-static int launch_gemm_t(const MmArgs& a, const void* x) {
-  using C = GemmCfg<BITS, MT, STAGES>;
+template <typename T, int BITS, bool ASYM, int STAGES>
+static int launch_gemm_sk_t(const MmArgs& a, const void* x, int ks) {
+  using C = GemmCfg<BITS, 1, STAGES>;
+  static_assert(STAGES * (C::A_BYTES + C::B_BYTES) >= 128 * 128 * 4, "the fp32 partial tile must fit the A/B stage buffers");
   CUtensorMap tmap;
   if (make_x_tmap(&tmap, x, a.M, a.K, a.dtype) != 0) return -1;
-  auto kern = gemm_kernel<T, BITS, ASYM, MT, STAGES>;
+  auto kern = gemm_sk_kernel<T, BITS, ASYM, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("b2q_gemm: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("b2q_gemm_sk: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  dim3 grid((a.N + G_BN - 1) / G_BN, (a.M + 128 * MT - 1) / (128 * MT), 1);
-  kern<<<grid, G_THREADS, C::SMEM_BYTES, a.stream>>>(tmap, (const uint4*)a.packed, (const T*)a.scales,
-                                                     (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M,
-                                                     a.K, a.N, a.group_size, gemm_gshc(a));
-  return (int)cudaGetLastError();
-}
-
-int launch_gemm(const MmArgs& a) {
-  if (a.K % G_BK != 0) {
-    set_error("b2q_gemm: K=%d must be a multiple of %d", a.K, G_BK);
+  const int nkb = a.K / G_BK;
+  const int kpc = (nkb + ks - 1) / ks;
+  if ((ks - 1) * kpc >= nkb) {
+    set_error("b2q_gemm_sk: ks=%d leaves a rank without k-blocks (K=%d)", ks, a.K);
     return -1;
   }
-  const void* x = a.x;
-  if (a.perm != nullptr) {
-    const size_t need = (size_t)a.M * a.K * 2;
-    if (a.workspace == nullptr || a.workspace_bytes < need) {
-      set_error("b2q_gemm: act-order needs a %zu-byte workspace (got %zu)", need, a.workspace_bytes);
-      return -1;
-    }
-    int e = launch_permute_cols(a.x, a.perm, a.workspace, a.M, a.K, a.stream);
-    if (e != 0) return e;
-    x = a.workspace;
-  }
-  if (a.M <= 128) {
-    // EXPERIMENTAL (round 1: compiled, not GPU-validated): cluster split-K so that small-M launches fill the GPU
-    const char* e = getenv("B2Q_GEMM_SPLITK");
-    if (e != nullptr && e[0] == '1') {
-      const int ks = gemm_sk_ranks(a.K, a.N);
-      if (ks > 1) return launch_gemm_sk(a, x, ks);
-    }
-  }
-  if (a.bits == 4 && a.M > 128 && a.tune_ks != -1)  // CTA-pair tier (tune_ks -1: force 1-CTA)
-    return a.sk_ws != nullptr ? launch_gemm2s(a, x, a.sk_ws) : launch_gemm2(a, x);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((a.N + G_BN - 1) / G_BN, 1, ks);
+  cfg.blockDim = dim3(G_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = ks;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, (const uint4*)a.packed, (const T*)a.scales,
+                                     (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M, a.K, a.N,
+                                     a.group_size, gemm_gshc(a), kpc);
+  return (int)e;
+}
+
+// x must already be the (act-order permuted, if any) activation matrix; M <= 128
+int launch_gemm_sk(const MmArgs& a, const void* x, int ks) {
   const bool asym = a.qzeros != nullptr;
-  const bool big = a.M > 128;
-#define B2Q_GEMM_CASE(T, BITS, ST)                                                              \
-  (asym ? (big ? launch_gemm_t<T, BITS, true, 2, ST>(a, x) : launch_gemm_t<T, BITS, true, 1, ST>(a, x)) \
-        : (big ? launch_gemm_t<T, BITS, false, 2, ST>(a, x) : launch_gemm_t<T, BITS, false, 1, ST>(a, x)))
-  if (a.dtype == 0) return a.bits == 4 ? B2Q_GEMM_CASE(__half, 4, 4) : B2Q_GEMM_CASE(__half, 8, 3);
-  return a.bits == 4 ? B2Q_GEMM_CASE(__nv_bfloat16, 4, 4) : B2Q_GEMM_CASE(__nv_bfloat16, 8, 3);
-#undef B2Q_GEMM_CASE
+#define B2Q_GSK(T, BITS, ST) (asym ? launch_gemm_sk_t<T, BITS, true, ST>(a, x, ks) : launch_gemm_sk_t<T, BITS, false, ST>(a, x, ks))
+  if (a.dtype == 0) return a.bits == 4 ? B2Q_GSK(__half, 4, 4) : B2Q_GSK(__half, 8, 3);
+  return a.bits == 4 ? B2Q_GSK(__nv_bfloat16, 4, 4) : B2Q_GSK(__nv_bfloat16, 8, 3);
+#undef B2Q_GSK
 }
 
 }  // namespace b2q

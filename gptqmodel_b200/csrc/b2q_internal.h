@@ -53,6 +53,8 @@ constexpr size_t GEMM2S_FLAG_BYTES = 4096;
 size_t gemm2s_workspace_bytes();
 int launch_gemm2s(const MmArgs& a, const void* x, void* ws);
 int gemm2s_debug_items(int M, int K, int N, int pair, int* plan5, int* items, int max_items);
+int gemm_sk_ranks(int K, int N);                            // b2q_gemm_sk.cu (experimental): cluster split-K, M <= 128
+int launch_gemm_sk(const MmArgs& a, const void* x, int ks);
 int gemm_gshc(const MmArgs& a);  // 4-bit, CTA-pair (cta_group::2) tier; x already permuted
 int launch_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs,
                      size_t flag_offset, int max_elems, void* seq, cudaStream_t stream);

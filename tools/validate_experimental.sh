@@ -5,6 +5,7 @@
 #
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh decode'
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh gemm'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh midm'
 #   /usr/local/graft/bin/gpurun --gpus 2 --timeout 600 -- 'bash tools/validate_experimental.sh tp 2'
 set -u
 mkdir -p gpurun_out
@@ -34,6 +35,13 @@ for f in ("gpurun_out/bench_dp.json", "gpurun_out/bench_sk.json"):
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+    ;;
+  midm)
+    # cluster split-K of the single-CTA tcgen05 tier (M <= 128 and all 8-bit shapes)
+    B2Q_GEMM_SPLITK=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/gsk_tests.log
+    for sk in 0 1; do
+      B2Q_GEMM_SPLITK=$sk timeout 200 python tools/microbench.py gemm 17 32 64 128 2>&1 | tail -24 | tee gpurun_out/gsk_bench_$sk.log
+    done
     ;;
   tp)
     N=${2:-2}
