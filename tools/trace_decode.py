@@ -31,6 +31,8 @@ for li in (6, 7):
     t = T[li] - base
     used = t[:, 0] > -1e8
     names = ["start", "issued", "gdc_wait", "staged"] + [f"t{i//2}{'b' if i%2 else 'a'}" for i in range(10)] + ["?", "end"]
+    if os.environ.get("B2Q_DECODE_V2") == "1":  # b2q_decode2.cu stamps: no per-tile epilogues
+        names[4], names[5] = "loop_done", "cta_reduced"
     print(f"layer {li}:  (ns relative to layer 6's first CTA start; min / median / max over CTAs)")
     for sl in range(16):
         col = t[:, sl][T[li][:, sl] > 0]

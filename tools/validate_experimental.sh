@@ -22,6 +22,12 @@ case "${1:-decode}" in
     timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err
     timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 > gpurun_out/bench_v2.json 2> gpurun_out/bench_v2.err
     tail -c 600 gpurun_out/bench_v1.json; echo; tail -c 600 gpurun_out/bench_v2.json
+    # 3. phase timelines of the two kernels on the widest layers (ns; min / median / max over CTAs)
+    for v in 0 1; do
+      for shape in "4096 14336" "14336 4096"; do
+        B2Q_DECODE_V2=$v timeout 120 python tools/trace_decode.py $shape 2>&1 | tail -24 | tee -a gpurun_out/trace_v$((v+1)).log
+      done
+    done
     ;;
   gemm)
     B2Q_GEMM2_STREAMK=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/sk_tests.log
