@@ -27,6 +27,15 @@ namespace b2q {
 
 constexpr int DEC_AR_MAXCTA = 160;  // flag columns per source rank (>= CTAs of one launch: 148)
 
+// Cluster barrier whose memory ordering is only CTA-scope: every cluster-scope release compiles to MEMBAR.ALL.GPU on
+// sm_100a (checked with cuobjdump), which waits on the whole memory system although the data exchanged here lives in
+// shared memory, whose single point of coherence is the owning SM.  MEMBAR.ALL.CTA makes this thread's shared-memory
+// stores (and outstanding DSMEM loads) performed before the relaxed arrive.  Weaker than the PTX model asks for:
+// selected only with B2Q_DECODE2_FASTSYNC=1 (A/B switch), default is cluster_sync_all().
+__device__ __forceinline__ void cluster_sync_cta_fenced() {
+  asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void dec_st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const uint32_t bars = bars0 + warp * DEC_STAGES * 8;
   const uint32_t xbar = bars0 + nwarps * DEC_STAGES * 8;
   const bool PERM = perm != nullptr;
-  const bool XTMA = xtma != 0 && !PERM;
+  const bool XTMA = (xtma & 1) != 0 && !PERM;  // xtma bit 0: bulk-copied activations, bit 1: CTA-fenced cluster barriers
 
   // ---- 1. the first ring stages of this warp requested before anything else -------------------------
   const int nq = (q0 + wg < q1) ? (q1 - q0 - wg + gw - 1) / gw : 0;  // quads per tile for this warp
@@ -397,14 +406,16 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   stamp(5);
   const int crank = nrank > 1 ? (int)cluster_ctarank() : 0;
   if (nrank > 1) {
-    cluster_sync_all();  // every rank's cpart is complete (also a CTA barrier)
+    if (xtma & 2) cluster_sync_cta_fenced();
+    else cluster_sync_all();  // every rank's cpart is complete (also a CTA barrier)
     for (int row = crank * nwarps + warp; row < rows; row += (int)nrank * nwarps) {
       if (!row_live(row)) continue;
       float v = 0.f;
       for (uint32_t r = 0; r < nrank; ++r) v += ld_dsmem_f32(smem_u32(&cpart[row * 32 + lane]), r);
       emit(row, v);
     }
-    cluster_sync_all();  // keep every rank's smem alive until all peers have read it
+    if (xtma & 2) cluster_sync_cta_fenced();
+    else cluster_sync_all();  // keep every rank's smem alive until all peers have read it
   }
   if (AR) {
     // ---- 5. all-reduce across GPUs over peer memory (the rows this CTA emitted are the rows it sums) ----
@@ -535,7 +546,7 @@ static int launch_decode2_t(const MmArgs& a, const DecSets& sets, const Decode2C
   int gsh = 31;  // per-channel: every k-block is group 0
   if (a.group_size == 64) gsh = 0;
   else if (a.group_size == 128) gsh = 1;
-  const int xtma = env_int("B2Q_DECODE2_XTMA", 1);
+  const int xtma = (env_int("B2Q_DECODE2_XTMA", 1) ? 1 : 0) | (env_int("B2Q_DECODE2_FASTSYNC", 0) ? 2 : 0);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sets, a.perm, (const T*)a.x, a.M, a.K, gsh, c.qpc, c.max_tiles, c.gw,
                                      c.stl, xtma, ar, (unsigned long long*)g_trace_ptr);
   return (int)e;

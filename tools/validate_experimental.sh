@@ -18,10 +18,13 @@ case "${1:-decode}" in
     for gw in 4 8; do
       B2Q_DECODE_V2=1 B2Q_DECODE2_GW=$gw timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "decode or cases or sibling" 2>&1 | tail -3 | tee -a gpurun_out/v2_tests.log
     done
+    B2Q_DECODE_V2=1 B2Q_DECODE2_FASTSYNC=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "decode or cases or sibling or llama" 2>&1 | tail -3 | tee -a gpurun_out/v2_tests.log
     # 2. A/B: v1 vs v2 on the Llama-3-8B stack (same box, back to back)
     timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err
     timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 > gpurun_out/bench_v2.json 2> gpurun_out/bench_v2.err
-    tail -c 600 gpurun_out/bench_v1.json; echo; tail -c 600 gpurun_out/bench_v2.json
+    B2Q_DECODE2_FASTSYNC=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 > gpurun_out/bench_v2_fastsync.json 2> gpurun_out/bench_v2_fastsync.err
+    B2Q_DECODE2_XTMA=0 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 > gpurun_out/bench_v2_ldg.json 2> gpurun_out/bench_v2_ldg.err
+    for f in v1 v2 v2_fastsync v2_ldg; do echo "== $f"; tail -c 700 gpurun_out/bench_$f.json | head -c 700; echo; done
     # 3. phase timelines of the two kernels on the widest layers (ns; min / median / max over CTAs)
     for v in 0 1; do
       for shape in "4096 14336" "14336 4096"; do
