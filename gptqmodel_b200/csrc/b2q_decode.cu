@@ -362,17 +362,20 @@ static bool decode_config(const MmArgs& a, int NT, DecodeCfg& best) {
   const int SMS = 148;
   double best_cost = 1e30;
   bool found = false;
+  static const bool two_groups = [] {  // read once: this runs on every launch
+    const char* eg = getenv("B2Q_DECODE_GROUPS");
+    return eg != nullptr && eg[0] == '2';
+  }();
   for (int ks = 1; ks <= 8; ks *= 2) {
     if (a.tune_ks > 0 && ks != a.tune_ks) continue;
     if (ks > quads) break;
     const int qpc = (quads + ks - 1) / ks;
     for (int warps = 4; warps <= DEC_MAX_WARPS; warps *= 2) {  // 4, 8, 16
       if (a.tune_warps > 0 && warps != a.tune_warps) continue;
-      const char* eg = getenv("B2Q_DECODE_GROUPS");
       // two independent 8-warp groups per CTA overlap one group's tile epilogue with the other's main loop (+5 % on the
       // Llama-3-8B step) but one full-size parity case failed with it in round 1: experimental, off by default
       int ngroups = 1;
-      if (eg != nullptr && eg[0] == '2' && warps == 16 && ks == 1) ngroups = 2;  // (the split-K + groups combination faults)
+      if (two_groups && warps == 16 && ks == 1) ngroups = 2;  // (the split-K + groups combination faults)
       const int gwarps = warps / ngroups;
       int C = SMS / ks;
       if (C * ngroups > NT) C = (NT + ngroups - 1) / ngroups;
