@@ -6,6 +6,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh decode'
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh gemm'
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh midm'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/validate_experimental.sh profile'
 #   /usr/local/graft/bin/gpurun --gpus 2 --timeout 600 -- 'bash tools/validate_experimental.sh tp 2'
 set -u
 mkdir -p gpurun_out
@@ -51,6 +52,17 @@ PY
     for sk in 0 1; do
       B2Q_GEMM_SPLITK=$sk timeout 200 python tools/microbench.py gemm 17 32 64 128 2>&1 | tail -24 | tee gpurun_out/gsk_bench_$sk.log
     done
+    ;;
+  profile)
+    # ncu captures of the new kernels (one GPU; numbers printed under ncu are never bench values).  Read them in the
+    # container with `ncu -i <rep> --page raw --csv` and summarise into profiles/r02_*.txt.
+    B2Q_DECODE_V2=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode2_kernel -c 3 \
+        -o gpurun_out/r02_decode2 -f python tools/prof_one.py gemv 4096 14336 > gpurun_out/ncu_decode2.log 2>&1
+    B2Q_GEMM2_STREAMK=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm2s_kernel -c 2 \
+        -o gpurun_out/r02_gemm2s -f python tools/prof_one.py gemm 4096 4096 2048 > gpurun_out/ncu_gemm2s.log 2>&1
+    B2Q_DECODE_V2=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+        --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --decode-v2 > gpurun_out/ncu_bench.log 2>&1
+    ls -la gpurun_out | tail -8
     ;;
   tp)
     N=${2:-2}
