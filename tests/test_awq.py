@@ -90,27 +90,3 @@ def test_awq_module_contract_without_gpu():
     from gptqmodel_b200 import B2QError
     with pytest.raises(B2QError):
         m.post_init()  # CPU tensors: converts, then fails loudly at the CUDA prepack (no CPU path)
-
-
-@pytest.mark.gpu
-def test_awq_module_matches_reference_outputs_on_gpu(awq_cases):
-    for name, c in awq_cases.items():
-        m = B200AwqQuantLinear.from_awq_tensors(c["qweight"], c["qzeros"], c["scales"], c["group_size"], bias=c["bias"])
-        y = m(c["x"].cuda())
-        assert_close_rel(y, c["y_fp16"], 1e-3, name)
-        ybf = m(c["x"].cuda().to(torch.bfloat16))
-        assert_close_rel(ybf, c["y_bf16"], 1.6e-2, name + " bf16")
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("K,N,gs", [(4096, 4096, 128), (4096, 14336, 64), (14336, 4096, 128)])
-def test_awq_full_size_layers_on_gpu(K, N, gs):
-    gen = torch.Generator(device="cuda").manual_seed(K + N)
-    qw = torch.randint(-(2 ** 31), 2 ** 31 - 1, (K, N // 8), dtype=torch.int32, device="cuda", generator=gen)
-    qz = torch.randint(-(2 ** 31), 2 ** 31 - 1, (K // gs, N // 8), dtype=torch.int32, device="cuda", generator=gen)
-    sc = (torch.rand(K // gs, N, device="cuda", generator=gen) * 0.01 + 0.005).to(torch.float16)
-    m = B200AwqQuantLinear.from_awq_tensors(qw, qz, sc, gs)
-    for M in (1, 7, 64, 300):
-        x = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).to(torch.float16)
-        ref = oracle.awq_forward(x.cpu(), qw.cpu(), qz.cpu(), sc.cpu(), gs)
-        assert_close_rel(m(x), ref, 1e-3, f"awq K={K} N={N} M={M}")

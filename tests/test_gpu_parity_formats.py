@@ -1,0 +1,53 @@
+"""GPU parity of the format front-ends: AWQ GEMM-format modules against outputs produced
+by the reference's own AwqTorchLinear, full-size AWQ layers against the oracle, and a checkpoint loaded from safetensors.
+
+Lives in its own file so that it is collected AFTER tests/test_gpu_parity.py (the hot path proper).
+"""
+import os
+
+import pytest
+import torch
+
+import oracle
+from gptqmodel_b200 import B200AwqQuantLinear, loader
+from helpers import assert_close_rel, make_layer
+from test_awq import awq_cases  # noqa: F401  (fixture)
+from test_loader import _ckpt_tensors, _write
+
+
+@pytest.mark.gpu
+def test_awq_module_matches_reference_outputs_on_gpu(awq_cases):
+    for name, c in awq_cases.items():
+        m = B200AwqQuantLinear.from_awq_tensors(c["qweight"], c["qzeros"], c["scales"], c["group_size"], bias=c["bias"])
+        y = m(c["x"].cuda())
+        assert_close_rel(y, c["y_fp16"], 1e-3, name)
+        ybf = m(c["x"].cuda().to(torch.bfloat16))
+        assert_close_rel(ybf, c["y_bf16"], 1.6e-2, name + " bf16")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,N,gs", [(4096, 4096, 128), (4096, 14336, 64), (14336, 4096, 128)])
+def test_awq_full_size_layers_on_gpu(K, N, gs):
+    gen = torch.Generator(device="cuda").manual_seed(K + N)
+    qw = torch.randint(-(2 ** 31), 2 ** 31 - 1, (K, N // 8), dtype=torch.int32, device="cuda", generator=gen)
+    qz = torch.randint(-(2 ** 31), 2 ** 31 - 1, (K // gs, N // 8), dtype=torch.int32, device="cuda", generator=gen)
+    sc = (torch.rand(K // gs, N, device="cuda", generator=gen) * 0.01 + 0.005).to(torch.float16)
+    m = B200AwqQuantLinear.from_awq_tensors(qw, qz, sc, gs)
+    for M in (1, 7, 64, 300):
+        x = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).to(torch.float16)
+        ref = oracle.awq_forward(x.cpu(), qw.cpu(), qz.cpu(), sc.cpu(), gs)
+        assert_close_rel(m(x), ref, 1e-3, f"awq K={K} N={N} M={M}")
+
+
+@pytest.mark.gpu
+def test_loaded_checkpoint_runs_on_gpu(tmp_path):
+    from helpers import assert_close_rel, oracle_forward
+    layers = {"m.q_proj": make_layer(512, 256, group_size=128, sym=True, seed=21),
+              "m.o_proj": make_layer(512, 128, group_size=64, sym=False, desc_act=True, bias=True, seed=22)}
+    cfg = {"bits": 4, "group_size": 128, "sym": True, "checkpoint_format": "gptq_v2",
+           "dynamic": {r".*o_proj": {"group_size": 64, "sym": False, "desc_act": True}}}
+    _write(str(tmp_path), {n: _ckpt_tensors(L) for n, L in layers.items()}, cfg)
+    mods = loader.load_quantized_linears(str(tmp_path), device="cuda")
+    x = (torch.randn(5, 512) * 0.5).to(torch.float16)
+    for n, L in layers.items():
+        assert_close_rel(mods[n](x.cuda()), oracle_forward(L, x), 1e-3, n)
