@@ -250,6 +250,28 @@ class B200QuantLinear(nn.Module):
             self.qzeros.data += off
             self._qzeros_format = 2
 
+    @torch.no_grad()
+    def pack_block(self, linear: nn.Module, scales: torch.Tensor, zeros: torch.Tensor, g_idx: torch.Tensor = None,
+                   **_ignored):
+        """Quantiser-side entry of the reference contract (`pack_block` / `pack_original` / `pack`,
+        qlinear/__init__.py:1326-1583): fill the checkpoint-layout tensors (v2 zero-points) from a float nn.Linear and
+        its [out_features, groups] scale / zero-point grids.  Runs on the weights' device (gptqmodel_b200/pack.py)."""
+        from .pack import pack_gptq
+
+        if self._prepacked:
+            raise B2QError("pack_block() after post_init()")
+        w = linear.weight.data
+        if g_idx is None:
+            g_idx = torch.arange(self.in_features, dtype=torch.int32, device=w.device) // self.group_size
+        out = pack_gptq(w, scales, zeros, g_idx, self.bits, bias=getattr(linear, "bias", None))
+        mk = lambda t: None if t is None else nn.Parameter(t, requires_grad=False)  # noqa: E731
+        self.qweight, self.qzeros, self.scales, self.g_idx = (mk(out[k]) for k in ("qweight", "qzeros", "scales", "g_idx"))
+        self.bias = mk(out["bias"])
+        self._qzeros_format = 2
+
+    pack = pack_block
+    pack_original = pack_block
+
     def list_buffers(self):
         out, seen = [], set()
         for state in (self._parameters, self._buffers):
