@@ -442,6 +442,43 @@ class B200QuantLinear(nn.Module):
         m.post_init()
         return m
 
+    @classmethod
+    def validate_device(cls, device) -> None:
+        """Reference contract (qlinear/__init__.py validate_device): raise if the module cannot live on `device`."""
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type != "cuda":
+            raise NotImplementedError(f"{cls.__name__} supports CUDA devices only, got `{dev}`")
+
+    @torch.no_grad()
+    def dequantize_weight(self, num_itr: int = 1, chunk: int = 2048) -> torch.Tensor:
+        """Dense W [in_features, out_features] in the scales' dtype, identical to the reference's
+        `dequantize_weight()` (qlinear/__init__.py:947-1021): rows of the identity are pushed through the tensor-core
+        tier, whose operands are the exact `(q - z) * s` values (one rounding), so every output element is one weight
+        times 1.0 plus zeros.  After post_init() only (the checkpoint-layout tensors are released there)."""
+        if not self._prepacked:
+            raise B2QError("dequantize_weight() before post_init()")
+        K, N = self.in_features, self.out_features
+        dt = self.scales.dtype
+        dev = self.packed.device
+        out = torch.empty((K, N), dtype=dt, device=dev)
+        chunk = max(256, chunk)  # > 128 rows: always the exact-dequant tensor-core tiers, never the decode tier
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for k0 in range(0, K, chunk):
+            rows = min(chunk, K - k0)
+            if rows <= 128:  # short tail: widen the block backwards so the tier stays the same
+                k0, rows = max(0, K - 256), min(256, K)
+            x = torch.zeros((rows, K), dtype=dt, device=dev)
+            x[torch.arange(rows, device=dev), torch.arange(k0, k0 + rows, device=dev)] = 1
+            ws, ws_bytes = None, 0
+            if self.perm is not None:
+                ws_bytes = lib.b2q_workspace_bytes(rows, K, N, 1)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            y = out[k0:k0 + rows]
+            check(lib.b2q_gemm(_ptr(x), _ptr(self.packed), _ptr(self._scales_for(dt)), _ptr(self._zeros_dev),
+                               _ptr(self.perm), None, _ptr(y), rows, K, N, self.bits, self.group_size, _DTYPE_CODE[dt],
+                               _ptr(ws), ws_bytes, stream), "b2q_gemm(dequantize_weight)")
+        return out
+
     def extra_repr(self) -> str:
         return (f"in_features={self.in_features}, out_features={self.out_features}, bits={self.bits}, "
                 f"group_size={self.group_size}, desc_act={self.desc_act}, sym={self.sym}")

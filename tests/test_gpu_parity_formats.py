@@ -51,3 +51,19 @@ def test_loaded_checkpoint_runs_on_gpu(tmp_path):
     x = (torch.randn(5, 512) * 0.5).to(torch.float16)
     for n, L in layers.items():
         assert_close_rel(mods[n](x.cuda()), oracle_forward(L, x), 1e-3, n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,gs,sym,desc", [(4, 128, True, False), (4, 64, False, True), (8, 32, False, False)])
+def test_dequantize_weight_bit_exact_on_gpu(bits, gs, sym, desc):
+    # reference contract: dequantize_weight() (qlinear/__init__.py:947-1021); identity rows through the exact-dequant tier
+    from gptqmodel_b200 import B200QuantLinear
+    L = make_layer(640, 96, bits=bits, group_size=gs, sym=sym, desc_act=desc, bias=True, seed=40 + bits)
+    m = B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], bits, gs,
+                                                bias=L["bias"], desc_act=desc, sym=sym)
+    W = m.dequantize_weight()
+    ref = oracle.dequantize_weight(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], bits)
+    assert W.shape == (640, 96) and W.dtype == torch.float16
+    assert torch.equal(W.cpu(), ref)
+    with pytest.raises(NotImplementedError):
+        B200QuantLinear.validate_device("cpu")
