@@ -88,6 +88,13 @@ def shard_rows(layer: Layer, rank: int, world: int) -> Layer:
     return out
 
 
+def shard_moe_expert(w1: Layer, w3: Layer, w2: Layer, rank: int, world: int):
+    """One expert of a Mixtral-style MoE block under tensor parallelism (BASELINE configs[4]):
+    w1 / w3 (gate / up) column-parallel, w2 (down) row-parallel — every rank keeps a slice of EVERY expert, so the block
+    needs one all-reduce of the combined output, exactly like a dense MLP."""
+    return shard_columns(w1, rank, world), shard_columns(w3, rank, world), shard_rows(w2, rank, world)
+
+
 def all_reduce_sum_(t: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     """The single collective of a row-parallel QuantLinear: in-place sum over the TP group (NCCL on GPUs)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

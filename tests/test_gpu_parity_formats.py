@@ -67,3 +67,33 @@ def test_dequantize_weight_bit_exact_on_gpu(bits, gs, sym, desc):
     assert torch.equal(W.cpu(), ref)
     with pytest.raises(NotImplementedError):
         B200QuantLinear.validate_device("cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [3, 40])
+def test_moe_block_on_gpu(T):
+    # BASELINE configs[4] in miniature: g64 asymmetric experts, top-2 routing, tokens grouped per expert (decode tier for
+    # small blocks with w1/w3 in one launch, tensor-core tier for larger ones); single GPU -> no collective
+    import torch.nn.functional as F
+    from gptqmodel_b200 import B200QuantLinear, moe
+    from helpers import oracle_forward
+    E, K, I, top_k = 4, 256, 512, 2
+    layers = [(make_layer(K, I, group_size=64, sym=False, seed=200 + 3 * e),
+               make_layer(K, I, group_size=64, sym=False, seed=201 + 3 * e),
+               make_layer(I, K, group_size=64, sym=False, seed=202 + 3 * e)) for e in range(E)]
+    mk = lambda L: B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], 4, 64,  # noqa: E731
+                                                           sym=False)
+    blk = moe.MoEExperts([mk(l[0]) for l in layers], [mk(l[1]) for l in layers], [mk(l[2]) for l in layers])
+    gen = torch.Generator().manual_seed(T)
+    x = (torch.randn(T, K, generator=gen) * 0.5).to(torch.float16)
+    ids, w = moe.route_topk(torch.randn(T, E, generator=gen), top_k)
+    ref = torch.zeros(T, K)
+    for t in range(T):
+        for j in range(top_k):
+            l1, l3, l2 = layers[int(ids[t, j])]
+            xt = x[t:t + 1]
+            h = (F.silu(oracle_forward(l1, xt).float()) * oracle_forward(l3, xt).float()).to(torch.float16)
+            ref[t] += float(w[t, j]) * oracle_forward(l2, h)[0].float()
+    got = blk(x.cuda(), ids.cuda(), w.cuda())
+    assert got.shape == (T, K) and got.dtype == torch.float16
+    assert_close_rel(got, ref, 4e-3, f"moe T={T}")   # two chained fp16 layers + fp16 silu: a few ulp on top of 1e-3

@@ -77,3 +77,61 @@ def test_tp2_sharding_and_allreduce_gloo():
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def _moe_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        import torch.nn.functional as F
+        from gptqmodel_b200 import moe, tp
+        from helpers import make_layer
+
+        E, K, I, T, top_k = 4, 128, 256, 9, 2     # Mixtral-style block in miniature: g64 asymmetric experts
+        layers = [(make_layer(K, I, group_size=64, sym=False, seed=100 + 3 * e),
+                   make_layer(K, I, group_size=64, sym=False, seed=101 + 3 * e),
+                   make_layer(I, K, group_size=64, sym=False, seed=102 + 3 * e)) for e in range(E)]
+
+        def dense(L):  # the oracle stands in for the kernel: [m, K] -> [m, N]
+            return lambda inp: oracle.forward(inp, L["qweight"], L["qzeros"], L["scales"], L["g_idx"], L["bits"],
+                                              bias=L["bias"])
+
+        gen = torch.Generator().manual_seed(4)
+        x = (torch.randn(T, K, generator=gen) * 0.5).to(torch.float16)
+        ids, w = moe.route_topk(torch.randn(T, E, generator=gen), top_k)
+        assert ids.shape == (T, top_k) and torch.allclose(w.sum(-1), torch.ones(T))
+        # straightforward per-token reference on the unsharded experts
+        ref = torch.zeros(T, K)
+        for t in range(T):
+            for j in range(top_k):
+                w1, w3, w2 = (dense(L) for L in layers[int(ids[t, j])])
+                xt = x[t:t + 1]
+                ref[t] += float(w[t, j]) * w2(F.silu(w1(xt)) * w3(xt))[0].float()
+        shards = [tp.shard_moe_expert(*layers[e], rank, world) for e in range(E)]
+        assert shards[0][0]["qweight"].shape[1] == I // world and shards[0][2]["qweight"].shape[0] == I // world * 4 // 32
+        blk = moe.MoEExperts([dense(s[0]) for s in shards], [dense(s[1]) for s in shards], [dense(s[2]) for s in shards])
+        got = blk(x, ids, w)                        # ends in ONE all-reduce over the TP group
+        err = (got.float() - ref).abs().max().item()
+        ok = err < 2e-2 * ref.abs().max().item()
+        # every rank holds the same result; an expert nobody routed to is skipped
+        outs = [torch.zeros_like(got) for _ in range(world)]
+        dist.all_gather(outs, got)
+        ok = ok and torch.equal(outs[0], outs[1])
+        only0 = torch.zeros(T, top_k, dtype=torch.long)
+        only0[:, 1] = 1
+        got2 = blk(x, only0, torch.full((T, top_k), 0.5))
+        ok = ok and torch.isfinite(got2.float()).all().item()
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_moe_block_tp2_gloo():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_moe_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
