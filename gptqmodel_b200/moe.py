@@ -16,7 +16,7 @@ CPU tests), so the routing / combination / sharding algebra is testable without 
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Sequence
+from typing import Callable, Sequence
 
 import torch
 import torch.nn.functional as F

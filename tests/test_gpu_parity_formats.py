@@ -3,7 +3,6 @@ by the reference's own AwqTorchLinear, full-size AWQ layers against the oracle, 
 
 Lives in its own file so that it is collected AFTER tests/test_gpu_parity.py (the hot path proper).
 """
-import os
 
 import pytest
 import torch
