@@ -142,3 +142,36 @@ def test_decode_allreduce_argument_validation_without_gpu():
     assert call(peer=(ctypes.c_void_p * 2)(16, None)) == -2 and b"peer buffer 1" in g.lib.b2q_last_error()
     assert call(bits=8) == -2 and b"bits=4" in g.lib.b2q_last_error()
     assert call(M=9, max_elems=9 * 4096, off=2 * 2 * 9 * 4096 * 4) == -2     # decode tier: <= 8 tokens
+
+
+def test_row_parallel_wrapper_and_moe_block_single_process():
+    # host logic without a process group: the wrappers fall through to the inner module / skip the collective
+    from gptqmodel_b200 import moe, tp
+
+    class Dense(torch.nn.Module):
+        def __init__(self, K, N, seed):
+            super().__init__()
+            self.w = (torch.randn(K, N, generator=torch.Generator().manual_seed(seed)) * 0.1)
+            self.perm, self.bits = None, 4
+
+        def forward(self, x):
+            return (x.float() @ self.w).to(x.dtype)
+
+    x = torch.randn(3, 16).to(torch.float16)
+    inner = Dense(16, 8, 0)
+    assert torch.equal(tp.RowParallelLinear(inner)(x), inner(x))
+    E = 3
+    blk = moe.MoEExperts([Dense(16, 32, 10 + e) for e in range(E)], [Dense(16, 32, 20 + e) for e in range(E)],
+                         [Dense(32, 16, 30 + e) for e in range(E)])
+    ids, w = moe.route_topk(torch.randn(3, E, generator=torch.Generator().manual_seed(1)), 2)
+    got = blk(x, ids, w)
+    ref = torch.zeros(3, 16)
+    for t in range(3):
+        for j in range(2):
+            e = int(ids[t, j])
+            xt = x[t:t + 1]
+            h = torch.nn.functional.silu(blk.w1[e](xt)) * blk.w3[e](xt)
+            ref[t] += float(w[t, j]) * blk.w2[e](h)[0].float()
+    assert torch.allclose(got.float(), ref, atol=2e-3, rtol=2e-2)
+    with pytest.raises(ValueError):
+        moe.MoEExperts([], [], [])
