@@ -1,6 +1,7 @@
 """GPU microbenchmarks used while tuning (not the contract bench; see bench.py).
 
   python tools/microbench.py gemv     sweep split-K cluster size / warps per Llama-3-8B shape (M=1)
+  python tools/microbench.py gemv2    same sweep for the experimental decode kernel v2 (+ warps per tile group), vs v1
   python tools/microbench.py gemm     time the tcgen05 GEMM at M=2048 per shape
 """
 import json
@@ -93,6 +94,59 @@ def gemv(MB=1):
         torch.cuda.empty_cache()
 
 
+def gemv2(MB=1):
+    """Sweep (split-K ranks, warps, warps per tile group) of the experimental decode kernel v2 per shape, against v1's
+    heuristic and v2's own planner choice: calibrates decode2_config's cost model (b2q_decode2.cu)."""
+    import ctypes
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    plan = (ctypes.c_int * 8)()
+    for K, N in SHAPES + [(4096, 6144), (4096, 28672)]:  # + the fused q|k|v and gate|up widths
+        nbytes = K * N // 2
+        copies = max(2, int(300e6 // nbytes) + 1)
+        mods = build(K, N, copies)
+        x = (torch.randn(MB, K, device="cuda") * 0.5).to(torch.float16)
+        out = torch.empty(MB, N, dtype=torch.float16, device="cuda")
+        alg = algorithmic_bytes(K, N, 128, 4, MB)
+
+        def run(ks, warps):
+            def fn():
+                st = torch.cuda.current_stream().cuda_stream
+                for m in mods:
+                    g.check(g.lib.b2q_decode(p(x), p(m.packed), p(m.scales.data), None, None, None, p(out), MB, K, N, 4,
+                                             128, 0, ks, warps, st), "decode")
+            return time_graph(fn) / copies
+
+        os.environ.pop("B2Q_DECODE2_GW", None)
+        os.environ["B2Q_DECODE_V2"] = "0"
+        v1 = run(0, 0)
+        os.environ["B2Q_DECODE_V2"] = "1"
+        v2 = run(0, 0)
+        g.lib.b2q_debug_decode_plan(2, MB, K, N, 0, 0, plan)
+        print(f"DECODE2 K={K} N={N} M={MB} alg={alg/1e6:.2f}MB  v1 {v1:.2f} us | v2 planner {v2:.2f} us "
+              f"(C={plan[0]} ks={plan[1]} warps={plan[2]} gw={plan[3]} tiles/group={plan[5]})  roofline "
+              f"{alg / PEAKS['hbm_gbs'] / 1e3:.2f} us")
+        res = []
+        for ks in (1, 2, 4, 8):
+            for warps in (8, 16):
+                for gw in (16, 8, 4, 2):
+                    if gw > warps or g.lib.b2q_debug_decode_plan(2, MB, K, N, ks, warps, plan) != 0:
+                        continue
+                    os.environ["B2Q_DECODE2_GW"] = str(gw)
+                    if g.lib.b2q_debug_decode_plan(2, MB, K, N, ks, warps, plan) != 0:
+                        continue
+                    try:
+                        res.append((run(ks, warps), ks, warps, gw, plan[5]))
+                    except Exception as e:  # noqa: BLE001
+                        print("   fail", ks, warps, gw, e)
+        os.environ.pop("B2Q_DECODE2_GW", None)
+        res.sort()
+        for us, ks, warps, gw, mt in res[:5]:
+            print(f"   ks={ks} warps={warps:2d} gw={gw:2d} tiles/group={mt:2d}  {us:7.2f} us  frac={alg/us/1e3/PEAKS['hbm_gbs']:.3f}")
+        del mods
+        torch.cuda.empty_cache()
+    os.environ["B2Q_DECODE_V2"] = "0"
+
+
 def gemm(Ms=(2048,)):
     for K, N in SHAPES:
         mods = build(K, N, 2)
@@ -117,5 +171,7 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemv"
     if what == "gemv":
         gemv(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    elif what == "gemv2":
+        gemv2(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     elif what == "gemm":
         gemm(tuple(int(a) for a in sys.argv[2:]) or (2048,))

@@ -26,6 +26,8 @@ case "${1:-decode}" in
     B2Q_DECODE2_FASTSYNC=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 > gpurun_out/bench_v2_fastsync.json 2> gpurun_out/bench_v2_fastsync.err
     B2Q_DECODE2_XTMA=0 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 > gpurun_out/bench_v2_ldg.json 2> gpurun_out/bench_v2_ldg.err
     for f in v1 v2 v2_fastsync v2_ldg; do echo "== $f"; tail -c 700 gpurun_out/bench_$f.json | head -c 700; echo; done
+    # 2b. per-shape sweep of v2's launch parameters against its planner's choice (cost-model calibration)
+    timeout 400 python tools/microbench.py gemv2 1 2>&1 | tail -50 | tee gpurun_out/v2_sweep.log
     # 3. phase timelines of the two kernels on the widest layers (ns; min / median / max over CTAs)
     for v in 0 1; do
       for shape in "4096 14336" "14336 4096"; do
