@@ -3,7 +3,7 @@
 # for sm_100a, their host logic and index arithmetic are covered by CPU tests, but they have never run on a GPU).
 # Run each block as ONE gpurun call; every command is wrapped in `timeout` so a protocol bug cannot hang the box.
 #
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh decode'
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/validate_experimental.sh decode'   (~20 GPU-min)
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh gemm'
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh midm'
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/validate_experimental.sh profile'
