@@ -36,8 +36,9 @@ class SiblingGroup:
 
     The first member called with a new `x` launches `b2q_decode_multi` for all members and parks the siblings'
     outputs; each sibling's `forward(x)` then just picks its result up.  Every module keeps the reference's
-    per-module `forward(x) -> y` contract (results are bit-identical to separate calls); only the launch count
-    changes.  This is SURVEY.md §8 row f1 ("fused neighbours of the GEMM").
+    per-module `forward(x) -> y` contract (same arithmetic; bit-identical to separate calls whenever the fused launch
+    splits K like the single launches would, see `b2q_debug_decode_plan`); only the launch count changes.  This is
+    SURVEY.md §8 row f1 ("fused neighbours of the GEMM").
 
     Contract: parked outputs are keyed on (data_ptr, version, M, dtype) of the activations, are handed out once, and
     are dropped as soon as any member is called with different activations.  Under `torch.inference_mode()` tensors
