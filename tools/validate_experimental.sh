@@ -3,6 +3,7 @@
 # for sm_100a, their host logic and index arithmetic are covered by CPU tests, but they have never run on a GPU).
 # Run each block as ONE gpurun call; every command is wrapped in `timeout` so a protocol bug cannot hang the box.
 #
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/validate_experimental.sh sanitize'   (first!)
 #   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/validate_experimental.sh decode'   (~20 GPU-min)
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh gemm'
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh midm'
@@ -53,6 +54,15 @@ PY
     B2Q_GEMM_SPLITK=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/gsk_tests.log
     for sk in 0 1; do
       B2Q_GEMM_SPLITK=$sk timeout 200 python tools/microbench.py gemm 17 32 64 128 2>&1 | tail -24 | tee gpurun_out/gsk_bench_$sk.log
+    done
+    ;;
+  sanitize)
+    # first contact with the hardware: small shapes under compute-sanitizer (memcheck finds the out-of-bounds smem /
+    # global accesses an index slip would cause, synccheck the barrier misuse, racecheck shared-memory hazards)
+    export B2Q_DECODE_V2=1 B2Q_GEMM2_STREAMK=1 B2Q_GEMM_SPLITK=1
+    timeout 300 python tools/san_one.py 2>&1 | tail -15 | tee gpurun_out/san_plain.log
+    for tool in memcheck synccheck racecheck; do
+      timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/san_one.py 2>&1 | tail -40 | tee gpurun_out/san_$tool.log
     done
     ;;
   profile)
