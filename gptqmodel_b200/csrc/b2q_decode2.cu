@@ -473,11 +473,13 @@ static int env_int(const char* name, int dflt) {
 static bool decode2_config(const MmArgs& a, int NT, Decode2Cfg& best) {
   const int quads = a.K / 128;
   const int SMS = 148;
-  const int force_gw = env_int("B2Q_DECODE2_GW", 0);
+  const int force_gw = env_int("B2Q_DECODE2_GW", 0);  // A/B switches for whole-model runs (bench.py --decode-v2)
+  const int force_ks = env_int("B2Q_DECODE2_KS", 0);
   double best_cost = 1e30;
   bool found = false;
   for (int ks = 1; ks <= 8; ks *= 2) {
     if (a.tune_ks > 0 && ks != a.tune_ks) continue;
+    if (a.tune_ks <= 0 && force_ks > 0 && ks != force_ks && force_ks <= quads) continue;
     if (ks > quads) break;
     const int qpc = (quads + ks - 1) / ks;
     if ((ks - 1) * qpc >= quads) continue;  // the last rank would own no quads
