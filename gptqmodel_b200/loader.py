@@ -88,6 +88,9 @@ def parse_quant_config(raw: dict) -> QuantSpec:
     spec.lm_head = bool(d.get("lm_head", False))
     spec.dynamic = d.get("dynamic") or None
     spec.meta = dict(d.get("meta") or {})
+    pack_dtype = str(d.get("pack_dtype", "int32")).replace("torch.", "")
+    if pack_dtype != "int32":
+        raise NotImplementedError(f"pack_dtype `{pack_dtype}` is not supported (int32 words only, like Marlin / Swordfish)")
     if spec.method not in ("gptq", "awq"):
         raise NotImplementedError(f"quantisation method `{spec.method}` is outside this package (gptq, awq)")
     if spec.method == "gptq" and spec.format not in ("gptq", "gptq_v2"):

@@ -56,6 +56,9 @@ def test_config_spellings():
         loader.parse_quant_config({"bits": 4, "quant_method": "awq", "version": "gemv"})
     with pytest.raises(ValueError):
         loader.parse_quant_config({"bits": 4, "is_marlin_format": True})
+    with pytest.raises(NotImplementedError):
+        loader.parse_quant_config({"bits": 4, "pack_dtype": "int16"})
+    assert loader.parse_quant_config({"bits": 4, "pack_dtype": "torch.int32"}).bits == 4
 
 
 def test_dynamic_overrides_first_match_wins():
