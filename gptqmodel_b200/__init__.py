@@ -7,6 +7,7 @@ Public API:
 """
 from ._lib import ABI_VERSION, B2QError, LIB_PATH, SYMBOLS, check, lib  # noqa: F401
 from .qlinear import B200QuantLinear, SiblingGroup, fuse_siblings  # noqa: F401
+from .adapter import Lora  # noqa: F401
 from .awq import B200AwqQuantLinear, awq_gemm_to_gptq  # noqa: F401
 
-__all__ = ["B200QuantLinear", "B200AwqQuantLinear", "awq_gemm_to_gptq", "fuse_siblings", "SiblingGroup", "lib", "check", "B2QError", "LIB_PATH", "SYMBOLS", "ABI_VERSION"]
+__all__ = ["B200QuantLinear", "B200AwqQuantLinear", "awq_gemm_to_gptq", "Lora", "fuse_siblings", "SiblingGroup", "lib", "check", "B2QError", "LIB_PATH", "SYMBOLS", "ABI_VERSION"]

@@ -26,6 +26,7 @@ import torch.nn as nn
 import ctypes
 
 from ._lib import B2QError, check, lib
+from .adapter import Lora
 
 _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
 DECODE_MAX_M = 8
@@ -139,7 +140,7 @@ class B200QuantLinear(nn.Module):
     SUPPORTS_IN_FEATURES_DIVISIBLE_BY = [64]
     SUPPORTS_OUT_FEATURES_DIVISIBLE_BY = [32]
     SUPPORTS_PACK_DTYPES = [torch.int32]
-    SUPPORTS_ADAPTERS = []  # any object with .apply(x=, out=) works; see forward()
+    SUPPORTS_ADAPTERS = [Lora]  # gptqmodel_b200/adapter.py; any object with .apply(x=, out=) works, see forward()
     SUPPORTS_DEVICES = ["cuda"]
     SUPPORTS_PLATFORM = ["linux"]
     SUPPORTS_DTYPES = [torch.float16, torch.bfloat16]

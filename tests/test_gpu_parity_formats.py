@@ -96,3 +96,24 @@ def test_moe_block_on_gpu(T):
     got = blk(x.cuda(), ids.cuda(), w.cuda())
     assert got.shape == (T, K) and got.dtype == torch.float16
     assert_close_rel(got, ref, 4e-3, f"moe T={T}")   # two chained fp16 layers + fp16 silu: a few ulp on top of 1e-3
+
+
+@pytest.mark.gpu
+def test_lora_adapter_epilogue_on_gpu():
+    # forward() ends with adapter.apply(x=x, out=out) (reference contract, qlinear/marlin.py:333-335)
+    from gptqmodel_b200 import B200QuantLinear, Lora
+    from helpers import oracle_forward
+    L = make_layer(512, 256, group_size=128, sym=True, bias=True, seed=77)
+    gen = torch.Generator().manual_seed(1)
+    A = (torch.randn(512, 8, generator=gen) * 0.05).to(torch.float16)
+    B = (torch.randn(8, 256, generator=gen) * 0.05).to(torch.float16)
+    m = B200QuantLinear(bits=4, group_size=128, desc_act=False, sym=True, in_features=512, out_features=256, bias=True,
+                        adapter=Lora(rank=8, lora_A=A, lora_B=B), register_buffers=False)
+    mk = lambda t: torch.nn.Parameter(t.clone().cuda(), requires_grad=False)  # noqa: E731
+    m.qweight, m.qzeros, m.scales, m.g_idx, m.bias = (mk(L[k]) for k in ("qweight", "qzeros", "scales", "g_idx", "bias"))
+    m.post_init()
+    for shape in ((1, 512), (2, 5, 512), (200, 512)):
+        x = (torch.randn(*shape, generator=gen) * 0.5).to(torch.float16)
+        base = oracle_forward(L, x.reshape(-1, 512))
+        ref = (base.float() + ((x.reshape(-1, 512).float() @ A.float()).to(torch.float16).float() @ B.float())).reshape(*shape[:-1], 256)
+        assert_close_rel(m(x.cuda()), ref, 2e-3, f"lora {shape}")

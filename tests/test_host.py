@@ -175,3 +175,31 @@ def test_row_parallel_wrapper_and_moe_block_single_process():
     assert torch.allclose(got.float(), ref, atol=2e-3, rtol=2e-2)
     with pytest.raises(ValueError):
         moe.MoEExperts([], [], [])
+
+
+def test_lora_adapter_matches_reference_arithmetic(tmp_path):
+    # adapter/adapter.py:150-178: out += (x @ lora_A) @ lora_B ; PEFT files hold the transposes
+    from safetensors.torch import save_file
+    from gptqmodel_b200.adapter import Lora
+    gen = torch.Generator().manual_seed(0)
+    K, N, r = 64, 32, 4
+    A, B = torch.randn(K, r, generator=gen).to(torch.float16), torch.randn(r, N, generator=gen).to(torch.float16)
+    x = torch.randn(2, 3, K, generator=gen).to(torch.float16)
+    out = torch.randn(2, 3, N, generator=gen).to(torch.float16)
+    ad = Lora(rank=r, lora_A=A, lora_B=B)
+    ad.post_init("model.layers.0.self_attn.q_proj", "cpu")
+    got = ad.apply(x=x, out=out.clone())
+    assert torch.equal(got, out + ((x.reshape(-1, K) @ A) @ B).view(2, 3, N))
+    save_file({"base_model.model.model.layers.0.self_attn.q_proj.lora_A.weight": A.T.contiguous(),
+               "base_model.model.model.layers.0.self_attn.q_proj.lora_B.weight": B.T.contiguous()},
+              str(tmp_path / "adapter_model.safetensors"))
+    ad2 = Lora(path=str(tmp_path))
+    ad2.post_init("model.layers.0.self_attn.q_proj", "cpu")
+    assert ad2.rank == r and torch.equal(ad2.lora_A, A) and torch.equal(ad2.lora_B, B)
+    assert ad2.apply(x=x.to(torch.bfloat16), out=out.to(torch.bfloat16).clone()).dtype == torch.bfloat16
+    assert ad2.lora_A.dtype == torch.bfloat16      # moved to the activations' dtype on first use, like the reference
+    with pytest.raises(KeyError):
+        Lora(path=str(tmp_path)).post_init("model.layers.9.mlp.up_proj", "cpu")
+    with pytest.raises(ValueError):
+        Lora(rank=8, lora_A=A, lora_B=B).post_init("x", "cpu")
+    assert Lora.name() == "lora" and Lora.parameter_keys() == ["lora_A", "lora_B"] and ad.to_dict()["rank"] == r
