@@ -117,3 +117,39 @@ def test_lora_adapter_epilogue_on_gpu():
         base = oracle_forward(L, x.reshape(-1, 512))
         ref = (base.float() + ((x.reshape(-1, 512).float() @ A.float()).to(torch.float16).float() @ B.float())).reshape(*shape[:-1], 256)
         assert_close_rel(m(x.cuda()), ref, 2e-3, f"lora {shape}")
+
+
+@pytest.mark.gpu
+def test_tiny_llama_with_b200_quantlinears_on_gpu():
+    # the caller side of the hot path: every nn.Linear of a (random-init) HF Llama replaced by a B200QuantLinear, q|k|v and
+    # gate|up fused into single decode launches; logits against the same model holding the dequantised dense weights
+    import torch.nn as nn
+    from gptqmodel_b200 import convert, fuse_siblings
+    from test_convert import tiny_llama
+    model, dense = tiny_llama(torch.float16), tiny_llama(torch.float16)
+    dense_w = {}
+
+    def factory(name, lin):
+        q = convert.quantize_linear(lin, bits=4, group_size=128, sym=("mlp" in name), device="cpu", name=name)
+        dense_w[name] = oracle.dequantize_weight(q.qweight.data, q.qzeros.data, q.scales.data, q.g_idx.data, 4).T.contiguous()
+        for k in ("qweight", "qzeros", "scales", "g_idx"):
+            setattr(q, k, nn.Parameter(getattr(q, k).data.cuda(), requires_grad=False))
+        q.post_init()
+        return q
+
+    swapped = convert.replace_linears(model, factory)
+    assert len(swapped) == 14
+    for name, W in dense_w.items():
+        dense.get_submodule(name).weight.data.copy_(W)
+    model, dense = model.cuda(), dense.cuda()
+    for layer in model.model.layers:
+        assert fuse_siblings([layer.self_attn.q_proj, layer.self_attn.k_proj, layer.self_attn.v_proj])
+        assert fuse_siblings([layer.mlp.gate_proj, layer.mlp.up_proj])
+    gen = torch.Generator().manual_seed(3)
+    for shape in ((2, 9), (1, 1), (3, 1)):     # prefill-like, single-token decode (fused launches), 3 sequences x 1 token
+        ids = torch.randint(0, 1000, shape, generator=gen).cuda()
+        with torch.inference_mode():
+            a = model(ids).logits.float()
+            b = dense(ids).logits.float()
+        assert a.shape == shape + (1000,) and torch.isfinite(a).all()
+        assert (a - b).abs().max().item() < 3e-2 * b.abs().max().item(), shape
