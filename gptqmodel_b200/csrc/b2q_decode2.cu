@@ -375,9 +375,11 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     r.idx = (size_t)m * tr.N + n;
     return r;
   };
+  bool pushed = false;  // this thread stored partial sums into peer memory
   auto emit = [&](int row, float v) {
     const RowRef r = row_ref(row);
     if (AR) {
+      pushed = true;
       // the bias of a row-parallel layer lives on one rank only (tp.shard_rows): it joins that rank's partial sum
       if (r.bias != nullptr) v += E::to_f(*r.bias);
       const size_t o = (ar_slot + ar.rank) * (size_t)ar.max_elems + r.idx;
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   }
   if (AR) {
     // ---- 5. all-reduce across GPUs over peer memory (the rows this CTA emitted are the rows it sums) ----
-    __threadfence_system();
+    if (pushed) __threadfence_system();  // only the (few) warps that pushed rows pay the system-scope membar
     __syncthreads();
     const int cta = (int)(blockIdx.y * gridDim.x + blockIdx.x);
     if ((int)threadIdx.x < ar.world) {
