@@ -3,7 +3,8 @@
 # for sm_100a, their host logic and index arithmetic are covered by CPU tests, but they have never run on a GPU).
 # Run each block as ONE gpurun call; every command is wrapped in `timeout` so a protocol bug cannot hang the box.
 #
-#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/validate_experimental.sh sanitize'   (first!)
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash tools/validate_experimental.sh all'        (first call: ~35 GPU-min)
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/validate_experimental.sh sanitize'   (if `all` shows failures)
 #   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/validate_experimental.sh decode'   (~20 GPU-min)
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh gemm'
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/validate_experimental.sh midm'
@@ -11,7 +12,32 @@
 #   /usr/local/graft/bin/gpurun --gpus 2 --timeout 600 -- 'bash tools/validate_experimental.sh tp 2'
 set -u
 mkdir -p gpurun_out
+summary() {  # one line per log: name + last line
+  for f in "$@"; do [ -f "$f" ] && echo "## $f: $(tail -1 "$f" | cut -c1-220)"; done
+}
 case "${1:-decode}" in
+  all)
+    # everything a first GPU call should answer, bounded: small-shape parity of all experimental kernels, then the GPU
+    # suite under each switch, then A/B bench lines.  ~35 GPU-min.  If san_plain fails, run `sanitize` next.
+    ( export B2Q_DECODE_V2=1 B2Q_GEMM2_STREAMK=1 B2Q_GEMM_SPLITK=1; timeout 300 python tools/san_one.py > gpurun_out/san_plain.log 2>&1 )
+    B2Q_DECODE_V2=1 timeout 700 python -m pytest tests -m gpu -x -q > gpurun_out/v2_tests.log 2>&1
+    B2Q_GEMM2_STREAMK=1 timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/sk_tests.log 2>&1
+    B2Q_GEMM_SPLITK=1 timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/gsk_tests.log 2>&1
+    timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err
+    timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --decode-v2 --gemm-streamk > gpurun_out/bench_v2sk.json 2> gpurun_out/bench_v2sk.err
+    for sk in 0 1; do B2Q_GEMM_SPLITK=$sk timeout 200 python tools/microbench.py gemm 17 64 128 > gpurun_out/gsk_bench_$sk.log 2>&1; done
+    summary gpurun_out/san_plain.log gpurun_out/v2_tests.log gpurun_out/sk_tests.log gpurun_out/gsk_tests.log
+    python - <<'PY'
+import json
+for f in ("gpurun_out/bench_v1.json", "gpurun_out/bench_v2sk.json"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, "decode tok/s", round(d["value"], 1), "roofline", d["roofline"]["frac"], "prefill", d.get("prefill"))
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
+    grep -h "GEMM M=" gpurun_out/gsk_bench_0.log gpurun_out/gsk_bench_1.log | head -40
+    ;;
   decode)
     # 1. parity: the whole GPU suite with every decode launch routed through b2q_decode2.cu
     B2Q_DECODE_V2=1 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/v2_tests.log
