@@ -470,12 +470,15 @@ def main():
                    if (args.decode_v2 or args.gemm_streamk or FUSED_AR is not None) else {}),
             },
             "roofline": {
-                "kernel": "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL); "
+                "kernel": ("decode2_kernel (EXPERIMENTAL b2q_decode2.cu: deferred tile epilogue, warp groups); "
+                           if args.decode_v2 else
+                           "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL); ")
                           + ("one launch per QuantLinear" if args.no_fuse else
                              "q/k/v and gate/up siblings share a launch: 4 launches per decoder layer"),
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                "algorithmic_bytes_per_launch": alg_bytes_step / n_launch, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
+                "traffic": None if args.decode_v2 else traffic,  # the ncu capture is of the default kernel
                 "traffic_note": "average per launch = measured DRAM/algorithmic ratio of the ncu --set full capture "
                                 "(profiles/r01_decode_final.txt: 30,318,080 B DRAM vs 30,539,776 B algorithmic for the "
                                 "4096x14336 launch) x algorithmic bytes per launch",
