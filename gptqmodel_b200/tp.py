@@ -146,6 +146,38 @@ class P2PAllReduce:
         return t
 
 
+def all_gather_last_dim(t: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Concatenate every rank's [..., n] slice along the last dimension (rank order); identity without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, t.contiguous(), group=group)
+    return torch.cat(parts, dim=-1)
+
+
+class GatheredColumnParallelLinear(torch.nn.Module):
+    """Tensor parallelism for an ACT-ORDER o_proj / down_proj, which `shard_rows` has to refuse (a row shard of an
+    act-order layer no longer holds whole quantisation groups; the reference's engines replicate the scale tables and
+    walk arbitrary g_idx instead, utils/marlin.py:296-305).  The layer is COLUMN-sharded (`shard_columns` keeps g_idx
+    whole, so any act-order layer qualifies) and wrapped as
+
+        x_shard [.., K/P] --all-gather--> x [.., K] --inner (N/P output features)--> y_shard --all-gather--> y [.., N]
+
+    i.e. two all-gathers of activation-sized tensors instead of one all-reduce; every rank ends with the full output,
+    exactly like RowParallelLinear, so the two are interchangeable inside a model."""
+
+    def __init__(self, inner: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, gather_input: bool = True):
+        super().__init__()
+        self.inner = inner
+        self.group = group
+        self.gather_input = gather_input
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.gather_input:
+            x = all_gather_last_dim(x, self.group)
+        return all_gather_last_dim(self.inner(x), self.group)
+
+
 class FusedDecodeAllReduce:
     """Symmetric buffers for `b2q_decode_allreduce`: the row-parallel QuantLinear and its all-reduce in ONE kernel.
 

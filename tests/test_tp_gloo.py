@@ -58,13 +58,25 @@ def _worker(rank, world, port, ret):
             outs = [torch.zeros_like(h) for _ in range(world)]
             dist.all_gather(outs, h)
             ok = ok and torch.equal(torch.cat(outs, dim=1), fwd(up, x))
-        # act-order row shards are refused loudly
+        # act-order row shards are refused loudly ...
         ao = make_layer(256, 128, group_size=64, desc_act=True, seed=3)
         try:
             tp.shard_rows(ao, rank, world)
             ok = False
         except NotImplementedError:
             pass
+        # ... and served column-parallel between two all-gathers instead (same interface: K/P in, full N out)
+        x = (torch.randn(3, 256, generator=torch.Generator().manual_seed(6)) * 0.5).to(torch.float16)
+        cs = tp.shard_columns(ao, rank, world)
+
+        class Inner(torch.nn.Module):
+            def forward(self, inp):
+                return oracle.forward(inp, cs["qweight"], cs["qzeros"], cs["scales"], cs["g_idx"], cs["bits"], bias=cs["bias"])
+
+        wrapped = tp.GatheredColumnParallelLinear(Inner())
+        got = wrapped(x[:, rank * 256 // world:(rank + 1) * 256 // world].contiguous())
+        full = oracle.forward(x, ao["qweight"], ao["qzeros"], ao["scales"], ao["g_idx"], ao["bits"], bias=ao["bias"])
+        ok = ok and torch.equal(got, full)
         ret[rank] = ok
     finally:
         dist.destroy_process_group()
