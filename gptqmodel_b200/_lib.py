@@ -19,6 +19,8 @@ SYMBOLS = {
     "b2q_last_error": (ctypes.c_char_p, []),
     "b2q_packed_bytes": (_sz, [_i, _i, _i]),
     "b2q_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b2q_mm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "b2q_debug_reload_env": (None, []),
     "b2q_prepack": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b2q_mm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b2q_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

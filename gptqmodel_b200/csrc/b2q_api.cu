@@ -16,6 +16,46 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+}
+
+static EnvCfg read_env() {
+  EnvCfg c;
+  c.disable_pdl = env_int("B2Q_DISABLE_PDL", 0);
+  c.gemm_1cta = env_int("B2Q_GEMM_1CTA", 0);
+  c.midm = env_int("B2Q_MIDM", 1);
+  c.decode_blocks_m = env_int("B2Q_DECODE_BLOCKS_M", 0);
+  c.decode_groups2 = env_int("B2Q_DECODE_GROUPS", 1) == 2;
+  c.gemm2_persist = env_int("B2Q_GEMM2_PERSIST", 1);
+  c.gemm2_dqw = env_int("B2Q_GEMM2_DQW", 8) == 4 ? 4 : 8;
+  c.midm_ks = env_int("B2Q_MIDM_KS", 0);
+  return c;
+}
+
+static EnvCfg g_env = read_env();  // once, at library load
+const EnvCfg& env() { return g_env; }
+void reload_env() { g_env = read_env(); }
+
+// Every entry point runs on the device that owns its pointers, whatever the caller's current device is (a module on
+// cuda:1 called while cuda:0 is current — ADVICE r01): switch for the duration of the call, restore afterwards.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(const void* p) {
+    cudaPointerAttributes at;
+    if (p != nullptr && cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+      dev = at.device;
+      if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev);
+      else prev = -1;
+    }
+    (void)cudaGetLastError();
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 static int check_cuda(int e, const char* what) {
   if (e > 0) set_error("%s: CUDA error %d (%s)", what, e, cudaGetErrorString((cudaError_t)e));
   return e;
@@ -74,10 +114,7 @@ static MmArgs make_args(const void* x, const void* packed, const void* scales, c
   a.tune_ks = 0;
   a.tune_warps = 0;
   a.sk_ws = nullptr;
-  {
-    const char* e = getenv("B2Q_DISABLE_PDL");
-    a.pdl = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
+  a.pdl = env().disable_pdl ? 0 : 1;
   return a;
 }
 }  // namespace b2q
@@ -116,9 +153,26 @@ const char* b2q_last_error(void) { return g_err; }
 size_t b2q_packed_bytes(int K, int N, int bits) { return (size_t)K * (size_t)N * (size_t)bits / 8; }
 
 size_t b2q_workspace_bytes(int M, int K, int N, int has_perm) {
+  // conservative (tier-independent) size: an act-order layer may need the permuted copy of x at ANY M >= 1 when no
+  // decode-tier configuration applies (8-bit, group_size 32, K % 128 != 0).  b2q_mm_workspace_bytes() is exact.
   (void)N;
-  return (has_perm && M > 1) ? (size_t)M * (size_t)K * 2 : 0;
+  return (has_perm && M >= 1) ? (size_t)M * (size_t)K * 2 : 0;
 }
+
+size_t b2q_mm_workspace_bytes(int M, int K, int N, int bits, int group_size, int has_perm) {
+  if (!has_perm || M < 1) return 0;
+  MmArgs a = {};
+  a.M = M;
+  a.K = K;
+  a.N = N;
+  a.bits = bits;
+  a.group_size = group_size;
+  if (decode_supported(a)) return 0;                 // the decode tier gathers x[perm] while staging the activations
+  if (M == 1 && bits == 8 && K % 128 == 0) return 0;  // so does the 8-bit GEMV
+  return (size_t)M * (size_t)K * 2;
+}
+
+void b2q_debug_reload_env(void) { reload_env(); }
 
 int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K, int N, int bits, void* stream) {
   if (qweight == nullptr || packed == nullptr) {
@@ -130,6 +184,7 @@ int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K
               N);
     return -2;
   }
+  DeviceGuard dg(packed);
   return check_cuda(launch_prepack(qweight, perm, packed, K, N, bits, (cudaStream_t)stream), "b2q_prepack");
 }
 
@@ -147,6 +202,7 @@ int b2q_allreduce(void* inout, int n, int dtype, int rank, int world, const void
       set_error("b2q_allreduce: peer buffer %d is NULL", i);
       return -2;
     }
+  DeviceGuard dg(inout);
   return check_cuda(launch_allreduce(inout, n, dtype, rank, world, peer_bufs, flag_offset, max_elems, seq,
                                      (cudaStream_t)stream), "b2q_allreduce");
 }
@@ -157,6 +213,7 @@ int b2q_decode_allreduce(const void* x, const void* packed, const void* scales, 
                          void* ctl, void* stream) {
   int v = validate("b2q_decode_allreduce", x, packed, scales, out, M, K, N, bits, group_size, dtype);
   if (v != 0) return v;
+  DeviceGuard dg(packed);
   if (peer_bufs == nullptr || ctl == nullptr || world < 2 || world > 8 || rank < 0 || rank >= world || max_elems <= 0 ||
       (size_t)M * (size_t)N > (size_t)max_elems || flag_offset % 16 != 0 ||
       flag_offset < (size_t)2 * world * (size_t)max_elems * sizeof(float)) {
@@ -196,6 +253,7 @@ int b2q_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K
     return -2;
   }
   if (M == 0) return 0;
+  DeviceGuard dg(out);
   return check_cuda(launch_permute_cols(x, perm, out, M, K, (cudaStream_t)stream), "b2q_permute_cols");
 }
 
@@ -204,6 +262,7 @@ int b2q_gemv(const void* x, const void* packed, const void* scales, const int32_
              void* stream) {
   int v = validate("b2q_gemv", x, packed, scales, out, 1, K, N, bits, group_size, dtype);
   if (v != 0) return v;
+  DeviceGuard dg(packed);
   if (ks > 16 || warps > 16 || (ks > 0 && (ks & (ks - 1)) != 0)) {
     set_error("b2q_gemv: ks=%d (power of two <= 16) / warps=%d (<= 16) out of range", ks, warps);
     return -2;
@@ -223,6 +282,7 @@ int b2q_decode(const void* x, const void* packed, const void* scales, const int3
                int warps, void* stream) {
   int v = validate("b2q_decode", x, packed, scales, out, M, K, N, bits, group_size, dtype);
   if (v != 0) return v;
+  DeviceGuard dg(packed);
   if (ks > 16 || warps > 16 || (ks > 0 && (ks & (ks - 1)) != 0)) {
     set_error("b2q_decode: ks=%d (power of two <= 16) / warps=%d (<= 16) out of range", ks, warps);
     return -2;
@@ -249,6 +309,7 @@ int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const 
   }
   int v = validate("b2q_decode_multi", x, packed[0], scales[0], out[0], M, K, N[0], bits, group_size, dtype);
   if (v != 0) return v;
+  DeviceGuard dg(packed[0]);
   MmArgs a = make_args(x, packed[0], scales[0], qzeros[0], nullptr, bias[0], out[0], M, K, N[0], bits, group_size,
                        dtype, nullptr, 0, stream);
   return check_cuda(launch_decode_multi(a, nsets, packed, scales, qzeros, bias, out, N), "b2q_decode_multi");
@@ -259,13 +320,11 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
              size_t workspace_bytes, void* stream) {
   int v = validate("b2q_gemm", x, packed, scales, out, M, K, N, bits, group_size, dtype);
   if (v != 0) return v;
+  DeviceGuard dg(packed);
   if (M == 0) return 0;
   MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
                        workspace_bytes, stream);
-  {
-    const char* e = getenv("B2Q_GEMM_1CTA");  // debugging / A-B measurements: keep the single-CTA tier
-    if (e != nullptr && e[0] == '1') a.tune_ks = -1;
-  }
+  if (env().gemm_1cta) a.tune_ks = -1;  // debugging / A-B measurements: keep the single-CTA tier
   return check_cuda(launch_gemm(a), "b2q_gemm");
 }
 
@@ -276,6 +335,7 @@ int b2q_gemm_streamk(const void* x, const void* packed, const void* scales, cons
                      void* workspace, size_t workspace_bytes, void* sk_workspace, void* stream) {
   int v = validate("b2q_gemm_streamk", x, packed, scales, out, M, K, N, bits, group_size, dtype);
   if (v != 0) return v;
+  DeviceGuard dg(packed);
   if (bits != 4 || M <= 128 || sk_workspace == nullptr || (reinterpret_cast<uintptr_t>(sk_workspace) & 15)) {
     set_error("b2q_gemm_streamk: needs bits=4, M > 128 and a 16-byte aligned stream-K workspace (got bits=%d M=%d)", bits,
               M);
@@ -300,18 +360,17 @@ int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t*
            size_t workspace_bytes, void* stream) {
   int v = validate("b2q_mm", x, packed, scales, out, M, K, N, bits, group_size, dtype);
   if (v != 0) return v;
+  DeviceGuard dg(packed);
   if (M == 0) return 0;
   MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
                        workspace_bytes, stream);
   if (decode_supported(a)) return check_cuda(launch_decode(a), "b2q_mm(decode)");
-  // small batches (9 <= M <= 16): two passes of the decode tier over blocks of 8 rows beat the single-CTA tcgen05 tier,
-  // whose grid of N/128 CTAs cannot fill 148 SMs (measured 28 us for 4096x4096 at any M <= 128 against 16.6 us here;
-  // at M = 32 the two are equal); the weights of the second pass come from L2.  A swapped-operand tcgen05 tier with
-  // cluster split-K is the planned replacement for 9 <= M <= 128.
+  // 9 <= M <= B2Q_DECODE_BLOCKS_M (default off): passes of the decode tier over blocks of 8 rows, the round-1 answer to
+  // the padded single-CTA tier's 28 us; superseded by the small-batch tier (b2q_midm.cu), kept for A/B measurements
   {
     MmArgs a8 = a;
     a8.M = 8;
-    if (M > 8 && M <= 16 && decode_supported(a8) && perm == nullptr) {
+    if (M > 8 && M <= env().decode_blocks_m && decode_supported(a8) && perm == nullptr) {
       for (int m0 = 0; m0 < M; m0 += 8) {
         MmArgs ab = a;
         ab.M = (M - m0 < 8) ? (M - m0) : 8;
@@ -324,10 +383,7 @@ int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t*
     }
   }
   if (M == 1 && bits == 8 && K % 128 == 0) return check_cuda(launch_gemv(a), "b2q_mm(gemv)");
-  {
-    const char* e = getenv("B2Q_GEMM_1CTA");
-    if (e != nullptr && e[0] == '1') a.tune_ks = -1;
-  }
+  if (env().gemm_1cta) a.tune_ks = -1;
   return check_cuda(launch_gemm(a), "b2q_mm(gemm)");
 }
 

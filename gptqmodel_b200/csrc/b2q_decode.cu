@@ -362,10 +362,7 @@ static bool decode_config(const MmArgs& a, int NT, DecodeCfg& best) {
   const int SMS = 148;
   double best_cost = 1e30;
   bool found = false;
-  static const bool two_groups = [] {  // read once: this runs on every launch
-    const char* eg = getenv("B2Q_DECODE_GROUPS");
-    return eg != nullptr && eg[0] == '2';
-  }();
+  const bool two_groups = env().decode_groups2 != 0;
   for (int ks = 1; ks <= 8; ks *= 2) {
     if (a.tune_ks > 0 && ks != a.tune_ks) continue;
     if (ks > quads) break;

@@ -15,8 +15,6 @@
 // mma.sync kernel (marlin_template.h) and Swordfish's CUTLASS-derived prefill tier (swordfish_prefill_*.cuh).
 #include <cuda.h>
 
-#include <cstdlib>
-
 #include "b2q_common.cuh"
 #include "b2q_dequant.cuh"
 #include "b2q_gemm.cuh"
@@ -289,7 +287,25 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_x_tmap(CUtensorMap* map, const void* x, int M, int K, int dtype) {
+// Tensor map of x [M, K] for boxes of (64 k) x (box_rows tokens), SWIZZLE_128B.  cuTensorMapEncodeTiled costs a few
+// microseconds of host time: maps are cached per thread on (pointer, M, K, dtype, box) — the encoded descriptor depends
+// on nothing else, so a hit is valid even if the allocation behind the pointer changed.
+int make_x_tmap_box(CUtensorMap* map, const void* x, int M, int K, int dtype, int box_rows) {
+  struct Entry {
+    const void* x;
+    int M, K, dtype, box;
+    CUtensorMap map;
+  };
+  constexpr int NCACHE = 16;
+  static thread_local Entry cache[NCACHE];
+  static thread_local int next = 0, filled = 0;
+  for (int i = 0; i < filled; ++i) {
+    const Entry& c = cache[i];
+    if (c.x == x && c.M == M && c.K == K && c.dtype == dtype && c.box == box_rows) {
+      *map = c.map;
+      return 0;
+    }
+  }
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) {
     set_error("b2q_gemm: cuTensorMapEncodeTiled not available from the driver");
@@ -297,17 +313,30 @@ int make_x_tmap(CUtensorMap* map, const void* x, int M, int K, int dtype) {
   }
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
   cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)G_BK, 128};
+  cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("b2q_gemm: cuTensorMapEncodeTiled failed (%d) for x=%p M=%d K=%d", (int)r, x, M, K);
+    set_error("b2q_gemm: cuTensorMapEncodeTiled failed (%d) for x=%p M=%d K=%d box=%d", (int)r, x, M, K, box_rows);
     return -1;
   }
+  Entry& e = cache[next];
+  e.x = x;
+  e.M = M;
+  e.K = K;
+  e.dtype = dtype;
+  e.box = box_rows;
+  e.map = *map;
+  next = (next + 1) % NCACHE;
+  if (filled < NCACHE) ++filled;
   return 0;
+}
+
+int make_x_tmap(CUtensorMap* map, const void* x, int M, int K, int dtype) {
+  return make_x_tmap_box(map, x, M, K, dtype, 128);
 }
 
 // log2(32-k chunks per group); 31 for per-channel (every chunk maps to group 0)
@@ -324,15 +353,8 @@ static int launch_gemm_t(const MmArgs& a, const void* x) {
   CUtensorMap tmap;
   if (make_x_tmap(&tmap, x, a.M, a.K, a.dtype) != 0) return -1;
   auto kern = gemm_kernel<T, BITS, ASYM, MT, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("b2q_gemm: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
-  }
+  static uint32_t smem_ok = 0;
+  if (int e = ensure_dyn_smem(kern, C::SMEM_BYTES, smem_ok, "b2q_gemm")) return e;
   dim3 grid((a.N + G_BN - 1) / G_BN, (a.M + 128 * MT - 1) / (128 * MT), 1);
   kern<<<grid, G_THREADS, C::SMEM_BYTES, a.stream>>>(tmap, (const uint4*)a.packed, (const T*)a.scales,
                                                      (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M,
@@ -356,14 +378,8 @@ int launch_gemm(const MmArgs& a) {
     if (e != 0) return e;
     x = a.workspace;
   }
-  if (a.M <= 128) {
-    // EXPERIMENTAL (round 1: compiled, not GPU-validated): cluster split-K so that small-M launches fill the GPU
-    const char* e = getenv("B2Q_GEMM_SPLITK");
-    if (e != nullptr && e[0] == '1') {
-      const int ks = gemm_sk_ranks(a.K, a.N);
-      if (ks > 1) return launch_gemm_sk(a, x, ks);
-    }
-  }
+  // M <= 128: small-batch tier (swapped operands, cluster split-K); B2Q_MIDM=0 keeps the round-1 padded single-CTA path
+  if (a.M <= 128 && env().midm && midm_supported(a)) return launch_midm(a, x);
   if (a.bits == 4 && a.M > 128 && a.tune_ks != -1)  // CTA-pair tier (tune_ks -1: force 1-CTA)
     return a.sk_ws != nullptr ? launch_gemm2s(a, x, a.sk_ws) : launch_gemm2(a, x);
   const bool asym = a.qzeros != nullptr;

@@ -457,35 +457,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_x_tmap_box(CUtensorMap* map, const void* x, int M, int K, int dtype, int box_rows);  // b2q_gemm.cu (cached)
 
 int make_x_tmap2(CUtensorMap* map, const void* x, int M, int K, int dtype) {
-  static EncodeTiledFn2 fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn2>(p);
-  }
-  if (fn == nullptr) {
-    set_error("b2q_gemm2: cuTensorMapEncodeTiled not available from the driver");
-    return -1;
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
-  cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)G2_BK, 128};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("b2q_gemm2: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return -1;
-  }
-  return 0;
+  return make_x_tmap_box(map, x, M, K, dtype, 128);
 }
 
 template <typename T, bool ASYM, int DQW>
@@ -493,15 +468,8 @@ static int launch_gemm2_t(const MmArgs& a, const void* x) {
   CUtensorMap tmap;
   if (make_x_tmap2(&tmap, x, a.M, a.K, a.dtype) != 0) return -1;
   auto kern = gemm2_kernel<T, ASYM, DQW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("b2q_gemm2: cannot opt in to %d bytes of shared memory: %s", G2_SMEM_BYTES, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
-  }
+  static uint32_t smem_ok = 0;
+  if (int e = ensure_dyn_smem(kern, G2_SMEM_BYTES, smem_ok, "b2q_gemm2")) return e;
   dim3 grid(2 * ((a.N + 255) / 256), (a.M + 255) / 256, 1);
   kern<<<grid, 64 + DQW * 32, G2_SMEM_BYTES, a.stream>>>(tmap, (const uint4*)a.packed, (const T*)a.scales,
                                                       (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M,
@@ -514,15 +482,8 @@ static int launch_gemm2p_t(const MmArgs& a, const void* x) {
   CUtensorMap tmap;
   if (make_x_tmap2(&tmap, x, a.M, a.K, a.dtype) != 0) return -1;
   auto kern = gemm2p_kernel<T, ASYM>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("b2q_gemm2p: cannot opt in to %d bytes of shared memory: %s", G2_SMEM_BYTES, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
-  }
+  static uint32_t smem_ok = 0;
+  if (int e = ensure_dyn_smem(kern, G2_SMEM_BYTES, smem_ok, "b2q_gemm2p")) return e;
   const int TM = (a.M + 255) / 256, TN = (a.N + 255) / 256;
   const int tiles = TM * TN;
   const int npairs = tiles < 74 ? tiles : 74;
@@ -535,20 +496,11 @@ static int launch_gemm2p_t(const MmArgs& a, const void* x) {
 // x must already be the (act-order permuted, if any) activation matrix
 int launch_gemm2(const MmArgs& a, const void* x) {
   const bool asym = a.qzeros != nullptr;
-  static int persist = -1;
-  if (persist < 0) {
-    const char* e = getenv("B2Q_GEMM2_PERSIST");
-    persist = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  if (persist) {
+  if (env().gemm2_persist) {
     if (a.dtype == 0) return asym ? launch_gemm2p_t<__half, true>(a, x) : launch_gemm2p_t<__half, false>(a, x);
     return asym ? launch_gemm2p_t<__nv_bfloat16, true>(a, x) : launch_gemm2p_t<__nv_bfloat16, false>(a, x);
   }
-  static int dqw = 0;
-  if (dqw == 0) {
-    const char* e = getenv("B2Q_GEMM2_DQW");
-    dqw = (e != nullptr && e[0] == '4') ? 4 : 8;
-  }
+  const int dqw = env().gemm2_dqw;
 #define B2Q_G2(T, AS) (dqw == 8 ? launch_gemm2_t<T, AS, 8>(a, x) : launch_gemm2_t<T, AS, 4>(a, x))
   if (a.dtype == 0) return asym ? B2Q_G2(__half, true) : B2Q_G2(__half, false);
   return asym ? B2Q_G2(__nv_bfloat16, true) : B2Q_G2(__nv_bfloat16, false);

@@ -112,6 +112,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 _SK_WORKSPACES = {}
+# EXPERIMENTAL switch, read once at import (never on the call path): stream-K work split of the CTA-pair prefill tier
+_STREAMK = os.environ.get("B2Q_GEMM2_STREAMK") == "1"
 
 
 def _streamk_workspace(device, stream) -> torch.Tensor:
@@ -375,10 +377,13 @@ class B200QuantLinear(nn.Module):
         if M == 0:
             return out.reshape(out_shape)
         ws, ws_bytes = None, 0
-        if self.perm is not None and M > 1:
-            ws_bytes = lib.b2q_workspace_bytes(M, K, N, 1)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        if M > 128 and self.bits == 4 and os.environ.get("B2Q_GEMM2_STREAMK") == "1":
+        if self.perm is not None:
+            # act-order: the tensor-core tiers read x[:, perm] from a workspace (the decode / GEMV tiers gather it while
+            # staging the activations and need none; b2q_mm_workspace_bytes mirrors b2q_mm's dispatch exactly)
+            ws_bytes = lib.b2q_mm_workspace_bytes(M, K, N, self.bits, self.group_size, 1)
+            if ws_bytes:
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        if M > 128 and self.bits == 4 and _STREAMK:
             # EXPERIMENTAL (round 1: compiled, not GPU-validated): stream-K work split of the CTA-pair prefill tier
             stream = torch.cuda.current_stream(x.device)
             check(

@@ -42,15 +42,22 @@ const char* b2q_last_error(void);
 /* Size in bytes of the prepacked weight buffer (== K*N*bits/8: the repack is a permutation). */
 size_t b2q_packed_bytes(int K, int N, int bits);
 
-/* Workspace b2q_mm needs for M rows (0 unless the layer has an act-order permutation and M > 1). */
+/* Workspace b2q_mm / b2q_gemm need for M rows.  b2q_workspace_bytes is the tier-independent upper bound (M*K*2 for any
+ * act-order layer, 0 otherwise); b2q_mm_workspace_bytes is exact for b2q_mm's own dispatch (0 when the decode / GEMV
+ * tiers, which gather x[perm] while staging the activations, serve the call). */
 size_t b2q_workspace_bytes(int M, int K, int N, int has_perm);
+size_t b2q_mm_workspace_bytes(int M, int K, int N, int bits, int group_size, int has_perm);
 
 /* Repack checkpoint-layout qweight into B2Q tiles.  perm (int32 [K], k' -> original row) may be NULL.
  * Requires K % 64 == 0, N % 32 == 0, bits in {4, 8}. */
 int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K, int N, int bits, void* stream);
 
-/* out[M, N] = x[M, K] @ dequant(W) (+ bias).  Dispatches on M inside the library (M <= 8: cluster split-K decode
- * tier, otherwise the tcgen05 GEMM) so a CUDA graph sees the true M.
+/* out[M, N] = x[M, K] @ dequant(W) (+ bias).  Dispatches on M inside the library so a CUDA graph sees the true M:
+ *   M <= 8 (4-bit, group 64|128|K)  : decode tier (mma.sync, cluster split-K)           b2q_decode.cu
+ *   M == 1 (8-bit)                  : CUDA-core GEMV                                     b2q_gemv.cu
+ *   M <= 128 otherwise              : small-batch tier (swapped tcgen05 operands, cluster split-K)  b2q_midm.cu
+ *   M  > 128                        : CTA-pair tcgen05 prefill tier (4-bit) / single-CTA tier (8-bit)
+ * The call runs on the device that owns `packed`, whatever the caller's current device is.
  *   x, scales, bias, out : fp16 (dtype 0) or bf16 (dtype 1), all the same type; x and out contiguous row-major
  *   qzeros               : NULL for symmetric layers (zero-point 2^(bits-1)), else int32 [G, N*bits/32]
  *   perm                 : NULL, or int32 [K] act-order permutation used at prepack
@@ -126,6 +133,10 @@ int b2q_decode_allreduce(const void* x, const void* packed, const void* scales, 
                          int rank, int world, const void* const* peer_bufs, size_t flag_offset, int max_elems,
                          void* ctl, void* stream);
 size_t b2q_decode_allreduce_flag_bytes(void);
+
+/* Debug / A-B tools: re-read the B2Q_* environment switches (they are read once when the library is loaded, never on the
+ * call path). */
+void b2q_debug_reload_env(void);
 
 /* Debug: device buffer (>= 148*16 uint64) receiving %globaltimer phase stamps of the decode kernel; NULL = off. */
 void b2q_debug_set_trace(void* device_buffer);

@@ -65,6 +65,18 @@ def oracle_forward(layer, x):
         bias=None if layer["bias"] is None else layer["bias"].cpu())
 
 
+PARITY_LOG = {}  # test id -> worst err/tol ratio seen by assert_close_rel (dumped by conftest at session end)
+
+
+def _record(what, rel, ratio):
+    import os
+    tid = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    e = PARITY_LOG.setdefault(tid, {"rel": rel, "worst_err_over_tol": 0.0, "worst_case": "", "checks": 0})
+    e["checks"] += 1
+    if ratio >= e["worst_err_over_tol"]:
+        e["worst_err_over_tol"], e["worst_case"], e["rel"] = round(ratio, 4), what, rel
+
+
 def assert_close_rel(out, ref, rel=1e-3, what=""):
     """|out - ref| <= rel * |ref| + rel * rms(ref): the north-star's "1e-3 rel fp16" with an absolute floor
     for outputs that cancel to ~0."""
@@ -75,5 +87,6 @@ def assert_close_rel(out, ref, rel=1e-3, what=""):
     err = (o - r).abs()
     tol = rel * r.abs() + rel * rms
     bad = err > tol
+    _record(what, rel, float((err / tol).max().item()) if err.numel() else 0.0)
     assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside {rel:g} rel; max abs err "
                            f"{err.max().item():.3e}, rms(ref) {rms:.3e}, worst ratio {(err / tol).max().item():.2f}")

@@ -138,6 +138,8 @@ CASES = [
     (4096, 1024, 4, 128, True, True, False),    # k/v proj with act-order (config 3)
     (3584, 4096, 4, 64, False, False, False),   # Mixtral TP-4 w2 shard, g64 asym (config 5)
     (1024, 96, 4, 128, True, False, False),     # N not a multiple of the 128-feature GEMM tile
+    (1024, 512, 4, 32, True, True, False),      # 4-bit g32 + act-order: no decode tier, M = 1 needs the x[perm] workspace
+    (1088, 160, 4, 64, False, False, True),     # K % 128 != 0 and a ragged last feature tile
 ]
 
 
@@ -190,6 +192,54 @@ def test_forward_matches_oracle_bf16(K, N, bits, gs, sym, desc, bias):
         # ABSOLUTE on |y|~1 with rtol 0.15 (tests/kernels/test_gptq.py:353-360)
 
 
+SMALL_BATCH_CASES = [
+    # K, N, bits, group, sym, desc_act, bias   (g32/g64/g128, sym/asym, 4/8-bit at every M below)
+    (1024, 512, 4, 32, True, False, False), (1024, 512, 4, 32, False, False, True),
+    (1024, 512, 4, 64, True, False, False), (2048, 384, 4, 64, False, True, False),
+    (1024, 512, 4, 128, True, False, True), (2048, 384, 4, 128, False, False, False),
+    (1024, 512, 8, 32, True, False, False), (1024, 512, 8, 32, False, False, True),
+    (1024, 512, 8, 64, False, False, False), (2048, 384, 8, 128, True, True, False),
+    (1024, 512, 8, 128, False, False, False), (512, 96, 4, -1, True, False, False),
+]
+
+
+@pytest.mark.parametrize("K,N,bits,gs,sym,desc,bias", SMALL_BATCH_CASES)
+def test_small_batch_tier_matches_oracle(K, N, bits, gs, sym, desc, bias):
+    """b2q_midm.cu (swapped tcgen05 operands + cluster split-K): every token-box width (16/32/64/128), partial boxes,
+    every split-K cluster size, through the module and the raw ABI."""
+    import gptqmodel_b200 as g
+    import os
+    L = make_layer(K, N, bits=bits, group_size=gs, sym=sym, desc_act=desc, bias=bias, seed=K + N + bits)
+    mod = _module(L)
+    gen = torch.Generator().manual_seed(45)
+    xs = (torch.randn(128, K, generator=gen) * 0.5).to(torch.float16)
+    ref = oracle_forward(L, xs)
+    for M in (9, 16, 17, 33, 64, 127, 128):
+        assert_close_rel(mod(xs[:M].to(DEV)), ref[:M], 1e-3, f"M={M}")
+    try:
+        for ks in (1, 2, 4, 8):
+            os.environ["B2Q_MIDM_KS"] = str(ks)
+            g.lib.b2q_debug_reload_env()
+            for M in (5, 33, 100):
+                assert_close_rel(_abi_call("gemm", mod, xs[:M].contiguous().to(DEV)), ref[:M], 1e-3, f"ks={ks} M={M}")
+    finally:
+        os.environ.pop("B2Q_MIDM_KS", None)
+        g.lib.b2q_debug_reload_env()
+    # determinism (no atomics: the split-K partials are summed in rank order)
+    a = mod(xs[:40].to(DEV))
+    assert torch.equal(a, mod(xs[:40].to(DEV)))
+    # the round-1 padded single-CTA tier (B2Q_MIDM=0) computes the same exact-dequant products: agree within fp32
+    # summation order
+    try:
+        os.environ["B2Q_MIDM"] = "0"
+        g.lib.b2q_debug_reload_env()
+        old = _abi_call("gemm", mod, xs[:40].contiguous().to(DEV))
+    finally:
+        os.environ.pop("B2Q_MIDM", None)
+        g.lib.b2q_debug_reload_env()
+    assert_close_rel(a, old, 1e-3, "midm vs padded tier")
+
+
 def test_batched_and_empty_shapes():
     L = make_layer(256, 128, seed=5, bias=True)
     mod = _module(L)
@@ -231,6 +281,8 @@ def test_llama3_8b_shapes_full_size(K, N):
     assert_close_rel(out, ref, 1e-3, "prefill M=2048")
     out1 = mod(x[5:6])
     assert_close_rel(out1, ref[5:6], 1e-3, "decode M=1")
+    for m in (16, 48, 128):  # small-batch tier at full size
+        assert_close_rel(mod(x[:m]), ref[:m], 1e-3, f"small batch M={m}")
     # size-independent properties: determinism and tier agreement
     assert torch.equal(mod(x[5:6]), out1)
     assert torch.equal(mod(x), out)

@@ -19,7 +19,14 @@ def test_awq_module_matches_reference_outputs_on_gpu(awq_cases):
     for name, c in awq_cases.items():
         m = B200AwqQuantLinear.from_awq_tensors(c["qweight"], c["qzeros"], c["scales"], c["group_size"], bias=c["bias"])
         y = m(c["x"].cuda())
-        assert_close_rel(y, c["y_fp16"], 1e-3, name)
+        # (a) the kernel against the fp32-accumulate oracle (itself pinned bit-exact to the reference's dequantize_gemm):
+        # the north-star bar
+        yo = oracle.awq_forward(c["x"], c["qweight"], c["qzeros"], c["scales"], c["group_size"], c["bias"])
+        assert_close_rel(y, yo, 1e-3, name)
+        # (b) the reference's own output: AwqTorchLinear on the CPU accumulates the matmul in fp16 (torch_awq.py:157-197),
+        # which differs from any fp32-accumulate result by up to ~1 fp16 ulp -> same bound as the GPTQ twin
+        # (test_gpu_parity.py::test_reference_generated_cases)
+        assert torch.allclose(y.float().cpu(), c["y_fp16"].float(), rtol=2e-3, atol=2e-3), name
         ybf = m(c["x"].cuda().to(torch.bfloat16))
         assert_close_rel(ybf, c["y_bf16"], 1.6e-2, name + " bf16")
 

@@ -25,7 +25,17 @@ def test_library_exports_every_declared_symbol():
 def test_abi_argument_validation_without_gpu():
     assert g.lib.b2q_packed_bytes(4096, 4096, 4) == 4096 * 4096 // 2
     assert g.lib.b2q_packed_bytes(256, 128, 8) == 256 * 128
-    assert g.lib.b2q_workspace_bytes(1, 4096, 4096, 1) == 0
+    assert g.lib.b2q_workspace_bytes(1, 4096, 4096, 1) == 4096 * 2  # tier-independent bound: any act-order layer, any M
+    # exact sizes for b2q_mm's own dispatch: the decode / GEMV tiers gather x[perm] themselves (a 4-bit g32
+    # act-order layer at M = 1 has no decode tier and must get its workspace)
+    assert g.lib.b2q_mm_workspace_bytes(1, 4096, 4096, 4, 128, 1) == 0
+    assert g.lib.b2q_mm_workspace_bytes(8, 4096, 4096, 4, 64, 1) == 0
+    assert g.lib.b2q_mm_workspace_bytes(1, 4096, 4096, 8, 128, 1) == 0
+    assert g.lib.b2q_mm_workspace_bytes(1, 4096, 4096, 4, 32, 1) == 4096 * 2
+    assert g.lib.b2q_mm_workspace_bytes(1, 4160, 4096, 4, 64, 1) == 4160 * 2   # K % 128 != 0
+    assert g.lib.b2q_mm_workspace_bytes(9, 4096, 4096, 4, 128, 1) == 9 * 4096 * 2
+    assert g.lib.b2q_mm_workspace_bytes(2, 4096, 4096, 8, 128, 1) == 2 * 4096 * 2
+    assert g.lib.b2q_mm_workspace_bytes(300, 4096, 4096, 4, 128, 0) == 0
     assert g.lib.b2q_workspace_bytes(16, 4096, 4096, 1) == 16 * 4096 * 2
     assert g.lib.b2q_workspace_bytes(16, 4096, 4096, 0) == 0
     assert g.lib.b2q_prepack(None, None, None, 64, 64, 4, None) == -2

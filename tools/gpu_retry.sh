@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: tools/gpu_retry.sh <log> <gpurun args...>   — retries while the pod answers "busy" (rc 3), nothing is charged for those
+log=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ] && ! grep -q "status=transient" "$log"; then echo "rc=$rc" >> "$log"; exit $rc; fi
+  sleep 90
+done

@@ -167,11 +167,55 @@ def gemm(Ms=(2048,)):
         torch.cuda.empty_cache()
 
 
+def midm(Ms=(9, 16, 32, 64, 128)):
+    """Small-batch tier (b2q_midm.cu) per Llama-3-8B shape with weights rotated > L2: heuristic split-K vs forced cluster
+    sizes vs the round-1 paths (padded single-CTA tier; decode row blocks for M <= 16), + 8-bit and group_size 32."""
+    def setenv(**kw):
+        for k in ("B2Q_MIDM", "B2Q_MIDM_KS", "B2Q_DECODE_BLOCKS_M"):
+            os.environ.pop(k, None)
+        os.environ.update({k: str(v) for k, v in kw.items()})
+        g.lib.b2q_debug_reload_env()
+
+    for bits, gs in ((4, 128), (4, 32), (8, 128)):
+        for K, N in SHAPES:
+            nbytes = K * N * bits // 8
+            copies = max(2, int(300e6 // nbytes) + 1)
+            mods = build(K, N, copies, bits=bits, gs=gs)
+            for M in ((1,) if (bits, gs) == (4, 32) else ()) + tuple(Ms) + ((2,) if bits == 8 else ()):
+                x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.float16)
+                alg = algorithmic_bytes(K, N, gs, bits, M)
+
+                def fn():
+                    for m in mods:
+                        m(x)
+                row = {}
+                variants = [("midm", {})] + [(f"ks{k}", {"B2Q_MIDM_KS": k}) for k in (1, 2, 4, 8)]
+                if (bits, gs) == (4, 128):
+                    variants.append(("padded_r1", {"B2Q_MIDM": 0}))
+                    if M <= 16:
+                        variants.append(("decode_x2_r1", {"B2Q_DECODE_BLOCKS_M": 16}))
+                for name, envs in variants:
+                    setenv(**envs)
+                    try:
+                        row[name] = time_graph(fn, iters=10) / copies
+                    except Exception as e:  # noqa: BLE001
+                        row[name] = float("nan")
+                        print("   fail", name, e)
+                setenv()
+                best = row["midm"]
+                print(f"MIDM bits={bits} g={gs} K={K} N={N} M={M}: " + "  ".join(f"{k} {v:6.2f}us" for k, v in row.items())
+                      + f"  | heuristic {alg / best / 1e3:6.0f} GB/s frac={alg / best / 1e3 / PEAKS['hbm_gbs']:.3f}", flush=True)
+            del mods
+            torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemv"
     if what == "gemv":
         gemv(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     elif what == "gemv2":
         gemv2(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    elif what == "midm":
+        midm(tuple(int(a) for a in sys.argv[2:]) or (9, 16, 32, 64, 128))
     elif what == "gemm":
         gemm(tuple(int(a) for a in sys.argv[2:]) or (2048,))
