@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2q.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/b2q.h declares: (restype, argtypes)
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
@@ -24,12 +24,9 @@ SYMBOLS = {
     "b2q_prepack": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b2q_mm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b2q_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "b2q_decode_multi": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b2q_decode_multi": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b2q_gemv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2q_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
-    "b2q_streamk_workspace_bytes": (_sz, []),
-    "b2q_gemm_streamk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
-    "b2q_debug_gemm_plan": (_i, [_i, _i, _i, _i, _vp, _vp, _i]),
     "b2q_allreduce": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
     "b2q_decode_allreduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
     "b2q_decode_allreduce_flag_bytes": (_sz, []),

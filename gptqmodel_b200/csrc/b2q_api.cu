@@ -113,7 +113,6 @@ static MmArgs make_args(const void* x, const void* packed, const void* scales, c
   a.stream = (cudaStream_t)stream;
   a.tune_ks = 0;
   a.tune_warps = 0;
-  a.sk_ws = nullptr;
   a.pdl = env().disable_pdl ? 0 : 1;
   return a;
 }
@@ -300,8 +299,8 @@ int b2q_decode(const void* x, const void* packed, const void* scales, const int3
 }
 
 int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const void* const* scales,
-                     const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* N, int M, int K,
-                     int bits, int group_size, int dtype, void* stream) {
+                     const int32_t* const* qzeros, const int32_t* perm, const void* const* bias, void* const* out,
+                     const int* N, int M, int K, int bits, int group_size, int dtype, void* stream) {
   if (x == nullptr || packed == nullptr || scales == nullptr || qzeros == nullptr || bias == nullptr ||
       out == nullptr || N == nullptr || nsets < 1) {
     set_error("b2q_decode_multi: null pointer argument");
@@ -310,7 +309,7 @@ int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const 
   int v = validate("b2q_decode_multi", x, packed[0], scales[0], out[0], M, K, N[0], bits, group_size, dtype);
   if (v != 0) return v;
   DeviceGuard dg(packed[0]);
-  MmArgs a = make_args(x, packed[0], scales[0], qzeros[0], nullptr, bias[0], out[0], M, K, N[0], bits, group_size,
+  MmArgs a = make_args(x, packed[0], scales[0], qzeros[0], perm, bias[0], out[0], M, K, N[0], bits, group_size,
                        dtype, nullptr, 0, stream);
   return check_cuda(launch_decode_multi(a, nsets, packed, scales, qzeros, bias, out, N), "b2q_decode_multi");
 }
@@ -326,33 +325,6 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
                        workspace_bytes, stream);
   if (env().gemm_1cta) a.tune_ks = -1;  // debugging / A-B measurements: keep the single-CTA tier
   return check_cuda(launch_gemm(a), "b2q_gemm");
-}
-
-size_t b2q_streamk_workspace_bytes(void) { return gemm2s_workspace_bytes(); }
-
-int b2q_gemm_streamk(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
-                     const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype,
-                     void* workspace, size_t workspace_bytes, void* sk_workspace, void* stream) {
-  int v = validate("b2q_gemm_streamk", x, packed, scales, out, M, K, N, bits, group_size, dtype);
-  if (v != 0) return v;
-  DeviceGuard dg(packed);
-  if (bits != 4 || M <= 128 || sk_workspace == nullptr || (reinterpret_cast<uintptr_t>(sk_workspace) & 15)) {
-    set_error("b2q_gemm_streamk: needs bits=4, M > 128 and a 16-byte aligned stream-K workspace (got bits=%d M=%d)", bits,
-              M);
-    return -2;
-  }
-  MmArgs a = make_args(x, packed, scales, qzeros, perm, bias, out, M, K, N, bits, group_size, dtype, workspace,
-                       workspace_bytes, stream);
-  a.sk_ws = sk_workspace;
-  return check_cuda(launch_gemm(a), "b2q_gemm_streamk");
-}
-
-int b2q_debug_gemm_plan(int M, int K, int N, int pair, int* plan5, int* items, int max_items) {
-  if (plan5 == nullptr || items == nullptr || M < 1 || K < 64 || K % 64 != 0 || N < 32 || max_items < 0) {
-    set_error("b2q_debug_gemm_plan: bad argument");
-    return -2;
-  }
-  return gemm2s_debug_items(M, K, N, pair, plan5, items, max_items);
 }
 
 int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,

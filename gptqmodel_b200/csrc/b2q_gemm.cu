@@ -381,7 +381,7 @@ int launch_gemm(const MmArgs& a) {
   // M <= 128: small-batch tier (swapped operands, cluster split-K); B2Q_MIDM=0 keeps the round-1 padded single-CTA path
   if (a.M <= 128 && env().midm && midm_supported(a)) return launch_midm(a, x);
   if (a.bits == 4 && a.M > 128 && a.tune_ks != -1)  // CTA-pair tier (tune_ks -1: force 1-CTA)
-    return a.sk_ws != nullptr ? launch_gemm2s(a, x, a.sk_ws) : launch_gemm2(a, x);
+    return launch_gemm2(a, x);
   const bool asym = a.qzeros != nullptr;
   const bool big = a.M > 128;
 #define B2Q_GEMM_CASE(T, BITS, ST)                                                              \

@@ -1,4 +1,4 @@
-// b2q_gemm.cuh — tile geometry shared by the single-CTA tcgen05 kernels (b2q_gemm.cu, b2q_gemm_sk.cu).
+// b2q_gemm.cuh — tile geometry shared by the single-CTA tcgen05 kernels (b2q_gemm.cu).
 #pragma once
 #include "b2q_common.cuh"
 

@@ -1,5 +1,5 @@
 // b2q_gemm2.cuh — constants and PTX wrappers shared by the CTA-pair (cta_group::2) prefill kernels
-// (b2q_gemm2.cu: one tile per pair / persistent pairs; b2q_gemm2s.cu: persistent pairs with stream-K work split).
+// (b2q_gemm2.cu: one tile per pair / persistent pairs).
 #pragma once
 #include <cuda.h>
 

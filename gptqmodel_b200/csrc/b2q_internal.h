@@ -23,7 +23,6 @@ struct MmArgs {
   int tune_ks;     // >0: force GEMV cluster size (split-K)
   int tune_warps;  // >0: force GEMV warps per CTA
   int pdl;         // 1: launch with programmatic stream serialization (default)
-  void* sk_ws;     // non-null: stream-K workspace (b2q_gemm_streamk), selects the experimental b2q_gemm2s.cu kernel
 };
 
 // Fused row-parallel all-reduce of the decode tier (b2q_decode2.cu).  world <= 1: plain decode.
@@ -52,14 +51,6 @@ bool midm_supported(const MmArgs& a);
 int midm_ranks(int K, int N);
 int launch_midm(const MmArgs& a, const void* x);
 int launch_gemm2(const MmArgs& a, const void* x);
-// stream-K variant of the CTA-pair tier (b2q_gemm2s.cu, experimental): ws = gemm2s_workspace_bytes() bytes, its first
-// GEMM2S_FLAG_BYTES zero when first used
-constexpr size_t GEMM2S_FLAG_BYTES = 4096;
-size_t gemm2s_workspace_bytes();
-int launch_gemm2s(const MmArgs& a, const void* x, void* ws);
-int gemm2s_debug_items(int M, int K, int N, int pair, int* plan5, int* items, int max_items);
-int gemm_sk_ranks(int K, int N);                            // b2q_gemm_sk.cu (experimental): cluster split-K, M <= 128
-int launch_gemm_sk(const MmArgs& a, const void* x, int ks);
 int gemm_gshc(const MmArgs& a);  // 4-bit, CTA-pair (cta_group::2) tier; x already permuted
 int launch_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs,
                      size_t flag_offset, int max_elems, void* seq, cudaStream_t stream);

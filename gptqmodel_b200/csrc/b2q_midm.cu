@@ -33,19 +33,26 @@ constexpr int MM_DQ_WARPS = 8;
 constexpr int MM_DQ_THREADS = MM_DQ_WARPS * 32;
 constexpr int MM_THREADS = 64 + MM_DQ_THREADS;
 
-template <int BITS, int NTOK, int STAGES>
+// Two rings.  The PACKED ring (PST stages: x tile + packed codes + scale / zero rows, 7-21 KB each) is what hides the HBM
+// latency: with 4 stages (the first version of this kernel) only 16 KB of weights per SM were in flight and every k-block
+// cost ~0.39 us = one HBM round trip / 4 (profiles/r02_midm_v1_bench.log: 25 us for the 64 k-blocks of 4096 x 4096 on one
+// CTA per tile); Little's law asks for ~43 KB per SM at 6.5 TB/s.  The DEQUANTISED ring (WST stages of 16 KB) only
+// decouples the dequant warps from the tensor core.
+template <int BITS, int NTOK, int PST, int WST>
 struct MidCfg {
   static constexpr int SUB = BITS / 4;
   static constexpr int W_BYTES = MM_BF * MM_BK * 2;      // dequantised weights, A operand: 16 KB
-  static constexpr int X_BYTES = NTOK * MM_BK * 2;       // activations, B operand
+  static constexpr int X_BYTES = NTOK * MM_BK * 2;       // activations, B operand (first in its stage: 1024-B aligned)
   static constexpr int P_CHUNK_BYTES = 4 * SUB * 512;    // 8-bit: 4 feature tiles (of 32) x 32 k
   static constexpr int P_BYTES = 2 * P_CHUNK_BYTES + (BITS == 4 ? 1024 : 0);  // + scale / zero rows (4-bit)
-  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES + P_BYTES;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int PSTAGE_BYTES = X_BYTES + P_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = WST * W_BYTES + PST * PSTAGE_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = NTOK < 32 ? 32 : NTOK;
   static constexpr int PART_BYTES = NTOK * MM_BF * 4;    // fp32 partial tile [token][feature]
-  static_assert(PART_BYTES <= STAGES * W_BYTES, "the fp32 partial tile reuses the weight stage buffers");
+  static_assert(PSTAGE_BYTES % 1024 == 0, "x tiles must stay 1024-byte aligned (SWIZZLE_128B atoms)");
+  static_assert(PART_BYTES <= WST * W_BYTES + PST * PSTAGE_BYTES, "the fp32 partial tile reuses the idle stage buffers");
+  static_assert((3 * PST + 2 * WST + 1) * 8 + 16 <= BAR_BYTES, "mbarrier area");
 };
 
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -57,24 +64,25 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-template <typename T, int BITS, bool ASYM, int NTOK, int STAGES>
+template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST>
 __global__ void __launch_bounds__(MM_THREADS, 1)
     midm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
                 const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, const T* __restrict__ bias,
                 T* __restrict__ out, int M, int K, int N, int gshc, int kpc) {
-  using C = MidCfg<BITS, NTOK, STAGES>;
+  using C = MidCfg<BITS, NTOK, PST, WST>;
   using E = ET<T>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const uint32_t sW = smem_base;                      // [STAGES][128 features][64 k]   (also: fp32 partial tile)
-  const uint32_t sX = sW + STAGES * C::W_BYTES;       // [STAGES][NTOK tokens][64 k]
-  const uint32_t sP = sX + STAGES * C::X_BYTES;       // [STAGES] packed codes (+ scale / zero rows)
-  const uint32_t sBar = sP + STAGES * C::P_BYTES;
-  const uint32_t bar_pfull = sBar, bar_xfull = sBar + 8 * STAGES, bar_wready = sBar + 16 * STAGES;
-  const uint32_t bar_empty = sBar + 24 * STAGES, bar_tfull = sBar + 32 * STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + (sBar - smem_base) + 32 * STAGES + 8);
+  const uint32_t sW = smem_base;                      // [WST][128 features][64 k]      (also: fp32 partial tile)
+  const uint32_t sR = sW + WST * C::W_BYTES;          // [PST]{ x tile [NTOK][64 k] | packed codes | scale / zero rows }
+  const uint32_t sBar = sR + PST * C::PSTAGE_BYTES;
+  const uint32_t bar_pfull = sBar, bar_xfull = sBar + 8 * PST, bar_pempty = sBar + 16 * PST;
+  const uint32_t bar_wready = sBar + 24 * PST, bar_wempty = bar_wready + 8 * WST, bar_tfull = bar_wempty + 8 * WST;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + (bar_tfull - smem_base) + 8);
+  auto sXs = [&](int s) { return sR + (uint32_t)s * C::PSTAGE_BYTES; };
+  auto sPs = [&](int s) { return sR + (uint32_t)s * C::PSTAGE_BYTES + C::X_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = N >> 5;
@@ -91,11 +99,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < PST; ++s) {
       mbar_init(bar_pfull + 8 * s, 1);
       mbar_init(bar_xfull + 8 * s, 1);
+      mbar_init(bar_pempty + 8 * s, MM_DQ_THREADS + 1);  // every dequant thread has read the codes + the MMA has read x
+    }
+    for (int s = 0; s < WST; ++s) {
       mbar_init(bar_wready + 8 * s, MM_DQ_THREADS);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_wempty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
     fence_mbar_init();
@@ -122,35 +133,35 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
           const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
           const int nrows = (g1 != g0) ? 2 : 1;
           mbar_expect_tx(bar_pfull + 8 * s, pbytes4 + nrows * (sbytes + zbytes));
-          bulk_load(sP + s * C::P_BYTES, packed + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_pfull + 8 * s);
+          bulk_load(sPs(s), packed + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_pfull + 8 * s);
           for (int r = 0; r < nrows; ++r) {
             const int gr = r ? g1 : g0;
-            bulk_load(sP + s * C::P_BYTES + 4096 + r * 320, scales + (size_t)gr * N + n0, sbytes, bar_pfull + 8 * s);
+            bulk_load(sPs(s) + 4096 + r * 320, scales + (size_t)gr * N + n0, sbytes, bar_pfull + 8 * s);
             if (ASYM)
-              bulk_load(sP + s * C::P_BYTES + 4096 + r * 320 + 256, qzeros + (size_t)gr * (N >> 3) + (n0 >> 3), zbytes,
+              bulk_load(sPs(s) + 4096 + r * 320 + 256, qzeros + (size_t)gr * (N >> 3) + (n0 >> 3), zbytes,
                         bar_pfull + 8 * s);
           }
         } else {
           mbar_expect_tx(bar_pfull + 8 * s, 2 * pbytes8);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            bulk_load(sP + s * C::P_BYTES + j * C::P_CHUNK_BYTES,
-                      packed + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes8, bar_pfull + 8 * s);
+            bulk_load(sPs(s) + j * C::P_CHUNK_BYTES, packed + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes8,
+                      bar_pfull + 8 * s);
         }
       };
       auto load_x = [&](int kb, int s) {
         mbar_expect_tx(bar_xfull + 8 * s, C::X_BYTES);
-        tma_load_2d(sX + s * C::X_BYTES, &tmap_x, bar_xfull + 8 * s, kb * MM_BK, 0);
+        tma_load_2d(sXs(s), &tmap_x, bar_xfull + 8 * s, kb * MM_BK, 0);
       };
-      // weights never depend on the previous kernel: the first STAGES blocks stream (and are dequantised) before the
+      // weights never depend on the previous kernel: the first PST blocks stream (and are dequantised) before the
       // producer of x has finished
-      const int pre = min(STAGES, nkb);
+      const int pre = min(PST, nkb);
       for (int i = 0; i < pre; ++i) load_weights(kb0 + i, i);
       asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int i = 0; i < pre; ++i) load_x(kb0 + i, i);
       for (int i = pre; i < nkb; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(bar_empty + 8 * s, ((i / STAGES) & 1) ^ 1);
+        const int s = i % PST;
+        mbar_wait(bar_pempty + 8 * s, ((i / PST) & 1) ^ 1);
         load_weights(kb0 + i, s);
         load_x(kb0 + i, s);
       }
@@ -159,17 +170,17 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = umma_idesc_f16(E::FMT, MM_BF, NTOK);
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      mbar_wait(bar_xfull + 8 * s, ph);
-      mbar_wait(bar_wready + 8 * s, ph);
+      const int s = i % PST, ws = i % WST;
+      mbar_wait(bar_xfull + 8 * s, (i / PST) & 1);
+      mbar_wait(bar_wready + 8 * ws, (i / WST) & 1);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t wdesc = umma_desc_k_sw128(sW + s * C::W_BYTES);
-        const uint64_t xdesc = umma_desc_k_sw128(sX + s * C::X_BYTES);
+        const uint64_t wdesc = umma_desc_k_sw128(sW + ws * C::W_BYTES);
+        const uint64_t xdesc = umma_desc_k_sw128(sXs(s));
 #pragma unroll
         for (int k = 0; k < MM_BK / 16; ++k) umma_f16(tbase, wdesc + 2 * k, xdesc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
-        umma_commit(bar_empty + 8 * s);
+        umma_commit(bar_wempty + 8 * ws);  // the dequantised stage may be overwritten
+        umma_commit(bar_pempty + 8 * s);   // the x tile of the packed stage has been read
         if (i == nkb - 1) umma_commit(bar_tfull);
       }
       __syncwarp();
@@ -184,9 +195,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
       const int lp = t & 31, g = lp >> 2, tt = lp & 3;
       const int f_lo = (t >> 5) * 16 + g, f_hi = f_lo + 8;
       for (int i = 0; i < nkb; ++i) {
-        const int kb = kb0 + i, s = i % STAGES;
-        mbar_wait(bar_pfull + 8 * s, (i / STAGES) & 1);
-        const uint8_t* pst = smem + (sP - smem_base) + s * C::P_BYTES;
+        const int kb = kb0 + i, s = i % PST, ws = i % WST;
+        mbar_wait(bar_pfull + 8 * s, (i / PST) & 1);
+        const uint8_t* pst = smem + (sPs(s) - smem_base);
         const uint4 pv = reinterpret_cast<const uint4*>(pst)[t];
         // this lane's 16 k of block kb lie in 32-k chunk 2*kb + (tt>>1)
         const int grow = ((2 * kb + (tt >> 1)) >> gshc) - ((2 * kb) >> gshc);  // 0 or 1
@@ -200,9 +211,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
           zl = (int)((zwl >> (4 * g)) & 15u);  // feature % 8 == g for both rows
           zh = (int)((zwh >> (4 * g)) & 15u);
         }
+        mbar_arrive(bar_pempty + 8 * s);  // codes + scales are in registers: the producer may refill the packed stage
         uint4 lo[2], hi[2];
         Dequant<T, 4>::run(pv, s_lo, zl, s_hi, zh, lo, hi);
-        const uint32_t rlo = sW + s * C::W_BYTES + f_lo * 128;
+        if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);  // the MMA of block i - WST has read the stage
+        const uint32_t rlo = sW + ws * C::W_BYTES + f_lo * 128;
         const uint32_t rhi = rlo + 8 * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -215,7 +228,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
                        : "memory");
         }
         fence_proxy_async_smem();
-        mbar_arrive(bar_wready + 8 * s);
+        mbar_arrive(bar_wready + 8 * ws);
       }
     } else {
       // 8-bit: thread = (feature row fr, 32-k half j of the block); two uint4 (16 k each) per stage
@@ -226,16 +239,21 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
       SZRaw cur = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb0 + j) >> gshc, nsafe, N), nxt = cur;
       const uint32_t sw = (uint32_t)(fr & 7);
       for (int i = 0; i < nkb; ++i) {
-        const int kb = kb0 + i, s = i % STAGES;
+        const int kb = kb0 + i, s = i % PST, ws = i % WST;
         if (i + 1 < nkb) nxt = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2 + j) >> gshc, nsafe, N);
-        mbar_wait(bar_pfull + 8 * s, (i / STAGES) & 1);
-        const uint32_t brow = sW + s * C::W_BYTES + fr * 128;
+        mbar_wait(bar_pfull + 8 * s, (i / PST) & 1);
+        const uint32_t brow = sW + ws * C::W_BYTES + fr * 128;
         int z = ZSYM;
         if (ASYM) z = (int)((cur.zw >> (BITS * (nsafe % PF))) & ((1u << BITS) - 1));
-        const uint4* pj = reinterpret_cast<const uint4*>(smem + (sP - smem_base) + s * C::P_BYTES + j * C::P_CHUNK_BYTES);
+        const uint4* pj = reinterpret_cast<const uint4*>(smem + (sPs(s) - smem_base) + j * C::P_CHUNK_BYTES);
+        uint4 pvs[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) pvs[h] = pj[(ntl * 2 + h) * 32 + lane];
+        mbar_arrive(bar_pempty + 8 * s);  // codes are in registers: the producer may refill the packed stage
+        if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint4 pv = pj[(ntl * 2 + h) * 32 + lane];
+          const uint4 pv = pvs[h];
           uint4 o[2];
           Dequant<T, 8>::run(pv, cur.s, z, o);
 #pragma unroll
@@ -247,7 +265,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(bar_wready + 8 * s);
+        mbar_arrive(bar_wready + 8 * ws);
         cur = nxt;
       }
     }
@@ -328,12 +346,12 @@ int midm_ranks(int K, int N) {
   return ks;
 }
 
-template <typename T, int BITS, bool ASYM, int NTOK, int STAGES>
+template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST>
 static int launch_midm_t(const MmArgs& a, const void* x, int ks) {
-  using C = MidCfg<BITS, NTOK, STAGES>;
+  using C = MidCfg<BITS, NTOK, PST, WST>;
   CUtensorMap tmap;
   if (make_x_tmap_box(&tmap, x, a.M, a.K, a.dtype, NTOK) != 0) return -1;
-  auto kern = midm_kernel<T, BITS, ASYM, NTOK, STAGES>;
+  auto kern = midm_kernel<T, BITS, ASYM, NTOK, PST, WST>;
   // the attribute is per device (a process may serve several GPUs): setting it is cheap, do it on every launch
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) {
@@ -370,14 +388,17 @@ int launch_midm(const MmArgs& a, const void* x) {
   const int nkb = a.K / MM_BK;
   while (ks > 1 && (ks - 1) * ((nkb + ks - 1) / ks) >= nkb) ks >>= 1;  // every rank needs at least one k-block
   const bool asym = a.qzeros != nullptr;
-#define B2Q_MM_NTOK(T, BITS, AS, ST128, ST)                                              \
-  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, ST>(a, x, ks)                            \
-   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, ST>(a, x, ks)                            \
-   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, ST>(a, x, ks)                            \
-               : launch_midm_t<T, BITS, AS, 128, ST128>(a, x, ks))
-#define B2Q_MM_CASE(T)                                                                   \
-  (a.bits == 4 ? (asym ? B2Q_MM_NTOK(T, 4, true, 4, 5) : B2Q_MM_NTOK(T, 4, false, 4, 5)) \
-               : (asym ? B2Q_MM_NTOK(T, 8, true, 4, 4) : B2Q_MM_NTOK(T, 8, false, 4, 4)))
+  // ring depths: M <= 32 keeps the CTA under ~111 KB of shared memory so that the NEXT kernel's CTAs (programmatic
+  // dependent launch) become resident — and stream their first weights — while this kernel still runs; wider token boxes
+  // take the whole SM and go deeper instead
+#define B2Q_MM_NTOK(T, BITS, AS)                                                                  \
+  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, (BITS == 4 ? 8 : 6), 3>(a, x, ks)                 \
+   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, (BITS == 4 ? 7 : 5), 3>(a, x, ks)                 \
+   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, (BITS == 4 ? 9 : 7), 3>(a, x, ks)                 \
+               : launch_midm_t<T, BITS, AS, 128, (BITS == 4 ? 6 : 5), 3>(a, x, ks))
+#define B2Q_MM_CASE(T)                                                          \
+  (a.bits == 4 ? (asym ? B2Q_MM_NTOK(T, 4, true) : B2Q_MM_NTOK(T, 4, false))   \
+               : (asym ? B2Q_MM_NTOK(T, 8, true) : B2Q_MM_NTOK(T, 8, false)))
   return a.dtype == 0 ? B2Q_MM_CASE(__half) : B2Q_MM_CASE(__nv_bfloat16);
 #undef B2Q_MM_CASE
 #undef B2Q_MM_NTOK

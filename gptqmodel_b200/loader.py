@@ -179,41 +179,48 @@ def load_quantized_linears(path: str, device="cuda", dtype: Optional[torch.dtype
         if fn is None:
             return None
         if fn not in handles:
-            handles[fn] = safe_open(fn, framework="pt")
+            handles[fn] = safe_open(fn, framework="pt").__enter__()
         return handles[fn].get_tensor(name)
 
     mods: Dict[str, nn.Module] = {}
-    for prefix in prefixes:
-        ms = spec.for_module(prefix)
-        if ms is None:
-            continue  # excluded by a negative dynamic pattern: stays a dense layer in the model
-        t = {s: tensor(f"{prefix}.{s}") for s in _TENSOR_SUFFIXES}
-        if t["qweight"] is None or t["qzeros"] is None or t["scales"] is None:
-            raise KeyError(f"{prefix}: checkpoint misses qweight / qzeros / scales")
-        mk = lambda x: None if x is None else nn.Parameter(x.contiguous().to(dev), requires_grad=False)  # noqa: E731
-        if ms.method == "awq":
-            K, N = t["qweight"].shape[0], t["qweight"].shape[1] * 32 // ms.bits
-            m = B200AwqQuantLinear(bits=ms.bits, group_size=ms.group_size, in_features=K, out_features=N,
-                                   bias=t["bias"] is not None, register_buffers=False, dtype=dtype, name=prefix)
-            m.qweight, m.qzeros, m.scales, m.bias = mk(t["qweight"]), mk(t["qzeros"]), mk(t["scales"]), mk(t["bias"])
-        else:
-            K, N = t["qweight"].shape[0] * 32 // ms.bits, t["qweight"].shape[1]
-            g_idx = t["g_idx"]
-            gs = ms.group_size if ms.group_size > 0 else K
-            if g_idx is None:
-                g_idx = (torch.arange(K, dtype=torch.int32) // gs)
-            m = B200QuantLinear(bits=ms.bits, group_size=ms.group_size, desc_act=ms.desc_act, sym=ms.sym, in_features=K,
-                                out_features=N, bias=t["bias"] is not None, register_buffers=False, dtype=dtype,
-                                name=prefix)
-            m.qweight, m.qzeros, m.scales = mk(t["qweight"]), mk(t["qzeros"]), mk(t["scales"])
-            m.g_idx, m.bias = mk(g_idx.to(torch.int32)), mk(t["bias"])
-            if ms.format == "gptq":
-                if not _v1_sym_ok(ms):
-                    raise ValueError(f"{prefix}: asymmetric checkpoint in GPTQ v1 format not written by gptqmodel >= 0.9.0 "
-                                     "(zero-points may have wrapped); the reference refuses it as well")
-                m.qzero_format(1)
-                m.convert_gptq_v1_to_v2()
-        if do_post:
-            m.post_init()
-        mods[prefix] = m
+    try:
+        for prefix in prefixes:
+            ms = spec.for_module(prefix)
+            if ms is None:
+                continue  # excluded by a negative dynamic pattern: stays a dense layer in the model
+            t = {s: tensor(f"{prefix}.{s}") for s in _TENSOR_SUFFIXES}
+            if t["qweight"] is None or t["qzeros"] is None or t["scales"] is None:
+                raise KeyError(f"{prefix}: checkpoint misses qweight / qzeros / scales")
+            mk = lambda x: None if x is None else nn.Parameter(x.contiguous().to(dev), requires_grad=False)  # noqa: E731
+            if ms.method == "awq":
+                K, N = t["qweight"].shape[0], t["qweight"].shape[1] * 32 // ms.bits
+                m = B200AwqQuantLinear(bits=ms.bits, group_size=ms.group_size, in_features=K, out_features=N,
+                                       bias=t["bias"] is not None, register_buffers=False, dtype=dtype, name=prefix)
+                m.qweight, m.qzeros, m.scales, m.bias = mk(t["qweight"]), mk(t["qzeros"]), mk(t["scales"]), mk(t["bias"])
+            else:
+                K, N = t["qweight"].shape[0] * 32 // ms.bits, t["qweight"].shape[1]
+                g_idx = t["g_idx"]
+                gs = ms.group_size if ms.group_size > 0 else K
+                if g_idx is None:
+                    g_idx = (torch.arange(K, dtype=torch.int32) // gs)
+                m = B200QuantLinear(bits=ms.bits, group_size=ms.group_size, desc_act=ms.desc_act, sym=ms.sym, in_features=K,
+                                    out_features=N, bias=t["bias"] is not None, register_buffers=False, dtype=dtype,
+                                    name=prefix)
+                m.qweight, m.qzeros, m.scales = mk(t["qweight"]), mk(t["qzeros"]), mk(t["scales"])
+                m.g_idx, m.bias = mk(g_idx.to(torch.int32)), mk(t["bias"])
+                if ms.format == "gptq":
+                    if not _v1_sym_ok(ms):
+                        raise ValueError(f"{prefix}: asymmetric checkpoint in GPTQ v1 format not written by gptqmodel >= 0.9.0 "
+                                         "(zero-points may have wrapped); the reference refuses it as well")
+                    m.qzero_format(1)
+                    m.convert_gptq_v1_to_v2()
+            if do_post:
+                m.post_init()
+            mods[prefix] = m
+    finally:
+        for h in handles.values():  # safe_open keeps the file mapped until closed
+            close = getattr(h, "__exit__", None)
+            if close is not None:
+                close(None, None, None)
+        handles.clear()
     return mods

@@ -42,15 +42,19 @@ class SiblingGroup:
     SURVEY.md §8 row f1 ("fused neighbours of the GEMM").
 
     Contract: parked outputs are keyed on (data_ptr, version, M, dtype) of the activations, are handed out once, and
-    are dropped as soon as any member is called with different activations.  Under `torch.inference_mode()` tensors
-    carry no version counter, so a sibling must not be called with NEW contents in the SAME buffer unless the member
-    that launched (the first one called, q_proj / gate_proj in HF decoder layers) ran on those contents first.
+    are dropped as soon as any member is called with different activations.  The group keeps a strong reference to the
+    activations it launched on until the parked outputs are consumed or replaced: while it is held the caching allocator
+    cannot hand that address to another tensor, so "same data_ptr" means "same tensor" even under
+    `torch.inference_mode()` (where tensors carry no version counter and fresh activations often reuse addresses).  What
+    remains undetectable there is an IN-PLACE overwrite of that very tensor between sibling calls; a member that finds
+    its own parked output already consumed (called twice on one key) therefore always relaunches.
     """
 
     def __init__(self, members):
         self.members = list(members)
         self.key = None
         self.pending = {}
+        self._x_ref = None  # pins the activations the parked outputs belong to
 
     @staticmethod
     def _version(t):
@@ -66,6 +70,7 @@ class SiblingGroup:
             out = self.pending.pop(id(who))
             if not self.pending:
                 self.key = None
+                self._x_ref = None
             return out
         mods = self.members
         n = len(mods)
@@ -78,10 +83,11 @@ class SiblingGroup:
         bias = vp(*[_ptr(m._bias_for(x2.dtype)) for m in mods])
         outp = vp(*[o.data_ptr() for o in outs])
         Ns = (ctypes.c_int * n)(*[m.out_features for m in mods])
-        check(lib.b2q_decode_multi(x2.data_ptr(), n, packed, scales, zeros, bias, outp, Ns, M, K, who.bits,
+        check(lib.b2q_decode_multi(x2.data_ptr(), n, packed, scales, zeros, _ptr(who.perm), bias, outp, Ns, M, K, who.bits,
                                    who.group_size, _DTYPE_CODE[x2.dtype],
                                    torch.cuda.current_stream(x2.device).cuda_stream), "b2q_decode_multi")
         self.key = key
+        self._x_ref = x2
         self.pending = {id(m): o for m, o in zip(mods, outs) if m is not who}
         return outs[mods.index(who)]
 
@@ -94,7 +100,11 @@ def fuse_siblings(mods) -> bool:
         return False
     m0 = mods[0]
     for m in mods:
-        if not isinstance(m, B200QuantLinear) or not m._prepacked or m.bits != 4 or m.perm is not None:
+        if not isinstance(m, B200KernelMixin) or not m._prepacked or m.bits != 4:
+            return False
+        # act-order siblings share a launch only if they share the permutation (q/k/v and gate/up of a GPTQ checkpoint
+        # are quantised against the same input Hessian, hence the same g_idx)
+        if (m.perm is None) != (m0.perm is None) or (m.perm is not None and not torch.equal(m.perm, m0.perm)):
             return False
         if (m.in_features, m.group_size, m._is_sym, m.packed.device, m.scales.dtype) != (
                 m0.in_features, m0.group_size, m0._is_sym, m0.packed.device, m0.scales.dtype):
@@ -111,45 +121,12 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-_SK_WORKSPACES = {}
-# EXPERIMENTAL switch, read once at import (never on the call path): stream-K work split of the CTA-pair prefill tier
-_STREAMK = os.environ.get("B2Q_GEMM2_STREAMK") == "1"
+class B200KernelMixin:
+    """State + behaviour of the B200 kernels behind the reference's QuantLinear contract, independent of the nn.Module
+    base it is mixed into: `B200QuantLinear` (stand-alone, below) and the subclass of the reference's own
+    `GPTQQuantLinear` that `gptqmodel_b200.reference_shim.make_reference_kernel` builds."""
 
-
-def _streamk_workspace(device, stream) -> torch.Tensor:
-    """One zero-filled stream-K workspace per (device, stream); owned by the library after the first use, never freed
-    (CUDA graphs may hold its address)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
-    ws = _SK_WORKSPACES.get(key)
-    if ws is None:
-        ws = torch.zeros(int(lib.b2q_streamk_workspace_bytes()), dtype=torch.uint8, device=device)
-        _SK_WORKSPACES[key] = ws
-    return ws
-
-
-class B200QuantLinear(nn.Module):
-    # ---- capability declaration (names follow the reference's BaseQuantLinear) ----
-    SUPPORTS_BACKENDS = ["b200"]
-    SUPPORTS_METHODS = ["gptq"]
-    SUPPORTS_FORMATS = {"gptq": 110, "gptq_v2": 110}  # > Swordfish (101) / Machete (100) / Marlin (90)
-    SUPPORTS_BITS = [4, 8]
-    SUPPORTS_GROUP_SIZE = [-1, 32, 64, 128]
-    SUPPORTS_DESC_ACT = [True, False]
-    SUPPORTS_SYM = [True, False]
-    SUPPORTS_SHARDS = True
-    SUPPORTS_TRAINING = False
-    SUPPORTS_AUTO_PADDING = False
-    SUPPORTS_IN_FEATURES_DIVISIBLE_BY = [64]
-    SUPPORTS_OUT_FEATURES_DIVISIBLE_BY = [32]
-    SUPPORTS_PACK_DTYPES = [torch.int32]
-    SUPPORTS_ADAPTERS = [Lora]  # gptqmodel_b200/adapter.py; any object with .apply(x=, out=) works, see forward()
-    SUPPORTS_DEVICES = ["cuda"]
-    SUPPORTS_PLATFORM = ["linux"]
-    SUPPORTS_DTYPES = [torch.float16, torch.bfloat16]
-    REQUIRES_FORMAT_V2 = True  # qzeros hold the true zero-point (loader adds 0x11111111 to v1 files)
-    QUANT_TYPE = "b200"
-
-    def __init__(
+    def _b200_setup(
         self,
         bits: int,
         group_size: int,
@@ -163,13 +140,9 @@ class B200QuantLinear(nn.Module):
         register_buffers: bool = True,
         **kwargs,
     ):
-        super().__init__()
-        ok, err = self.validate(
-            bits=bits, group_size=group_size, desc_act=desc_act, sym=sym, in_features=in_features,
-            out_features=out_features, pack_dtype=pack_dtype, dtype=kwargs.get("dtype"),
-        )
-        if not ok:
-            raise err
+        """Everything the kernels need on `self`; called by the constructor of the concrete class AFTER its nn.Module
+        base(s) are initialised (B200QuantLinear below, or the reference-side subclass of GPTQQuantLinear built by
+        gptqmodel_b200.reference_shim — which is why this is not a cooperative __init__)."""
         self.bits = bits
         self.requested_group_size = group_size
         self.group_size = group_size if group_size != -1 else in_features
@@ -181,11 +154,17 @@ class B200QuantLinear(nn.Module):
         self.pack_dtype_bits = 32
         self.pack_factor = 32 // bits
         self.maxq = (1 << bits) - 1
-        self.name = kwargs.get("name") or f"{self.__class__.__module__}.{self.__class__.__qualname__}"
-        self.backend = kwargs.get("backend", "b200")
+        if not hasattr(self, "name") or self.name is None:
+            self.name = kwargs.get("name") or f"{self.__class__.__module__}.{self.__class__.__qualname__}"
+        if not hasattr(self, "backend"):
+            self.backend = kwargs.get("backend", "b200")
         self.compute_dtype = kwargs.get("dtype") or torch.float16
-        self.adapter = adapter
-        self._qzeros_format = 2
+        if not hasattr(self, "adapter"):  # the reference's BaseQuantLinear keeps its own deep copy (qlinear/__init__.py:126)
+            self.adapter = adapter
+        # the reference's GPTQQuantLinear starts at format 1 and its loader flips it after converting the zero-points
+        # (utils/model.py:750-846); stand-alone modules are handed v2 tensors
+        if not hasattr(self, "_qzeros_format"):
+            self._qzeros_format = 2
         self._prepacked = False
         self._scales_cache = {}
         self._siblings = None
@@ -206,38 +185,6 @@ class B200QuantLinear(nn.Module):
         self.packed: Optional[torch.Tensor] = None
         self.perm: Optional[torch.Tensor] = None
         self._zeros_dev: Optional[torch.Tensor] = None
-
-    # ---- validation -------------------------------------------------------------------------------
-    @classmethod
-    def validate_once(cls) -> Tuple[bool, Optional[Exception]]:
-        if not torch.cuda.is_available():
-            return False, NotImplementedError("B200QuantLinear needs a CUDA device")
-        major, minor = torch.cuda.get_device_capability()
-        if major != 10:
-            return False, NotImplementedError(f"B200QuantLinear is built for sm_100a only, found sm_{major}{minor}")
-        return True, None
-
-    @classmethod
-    def validate(cls, bits: int, group_size: int = -1, desc_act: bool = False, sym: bool = True,
-                 in_features: int = None, out_features: int = None, pack_dtype: torch.dtype = None,
-                 dtype: Optional[torch.dtype] = None, **_ignored) -> Tuple[bool, Optional[Exception]]:
-        """Static parameter check; NotImplementedError means "unsupported here, try the next kernel"."""
-        if bits not in cls.SUPPORTS_BITS:
-            return False, NotImplementedError(f"{cls.__name__}: bits={bits} not in {cls.SUPPORTS_BITS}")
-        if group_size not in cls.SUPPORTS_GROUP_SIZE:
-            return False, NotImplementedError(f"{cls.__name__}: group_size={group_size} not in {cls.SUPPORTS_GROUP_SIZE}")
-        if pack_dtype is not None and pack_dtype not in cls.SUPPORTS_PACK_DTYPES:
-            return False, NotImplementedError(f"{cls.__name__}: pack_dtype={pack_dtype} unsupported")
-        if dtype is not None and dtype not in cls.SUPPORTS_DTYPES:
-            return False, NotImplementedError(f"{cls.__name__}: dtype={dtype} unsupported")
-        if in_features is not None:
-            if in_features % 64 != 0:
-                return False, NotImplementedError(f"{cls.__name__}: in_features={in_features} must be divisible by 64")
-            if group_size != -1 and in_features % group_size != 0:
-                return False, NotImplementedError(f"{cls.__name__}: in_features % group_size != 0")
-        if out_features is not None and out_features % 32 != 0:
-            return False, NotImplementedError(f"{cls.__name__}: out_features={out_features} must be divisible by 32")
-        return True, None
 
     def qzero_format(self, format: int = None) -> int:
         if format is None:
@@ -328,7 +275,10 @@ class B200QuantLinear(nn.Module):
         self.g_idx = nn.Parameter(torch.empty(0, dtype=torch.int32, device=dev), requires_grad=False)
         self.scales.data = self.scales.data.contiguous()
         self._prepacked = True
-        if self.adapter is not None and hasattr(self.adapter, "post_init"):
+        base_post_init = getattr(super(), "post_init", None)
+        if base_post_init is not None:
+            base_post_init()  # reference base: BaseQuantLinear.post_init() initialises the adapter (qlinear/__init__.py:224-234)
+        elif self.adapter is not None and hasattr(self.adapter, "post_init"):
             self.adapter.post_init(weight_key=self.name, device=dev,
                                    lora_A=getattr(self, "lora_A", None), lora_B=getattr(self, "lora_B", None))
 
@@ -383,20 +333,6 @@ class B200QuantLinear(nn.Module):
             ws_bytes = lib.b2q_mm_workspace_bytes(M, K, N, self.bits, self.group_size, 1)
             if ws_bytes:
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        if M > 128 and self.bits == 4 and _STREAMK:
-            # EXPERIMENTAL (round 1: compiled, not GPU-validated): stream-K work split of the CTA-pair prefill tier
-            stream = torch.cuda.current_stream(x.device)
-            check(
-                lib.b2q_gemm_streamk(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)),
-                                     _ptr(self._zeros_dev), _ptr(self.perm), _ptr(self._bias_for(x.dtype)), _ptr(out),
-                                     M, K, N, self.bits, self.group_size, _DTYPE_CODE[x.dtype], _ptr(ws), ws_bytes,
-                                     _ptr(_streamk_workspace(x.device, stream)), stream.cuda_stream),
-                "b2q_gemm_streamk",
-            )
-            out = out.reshape(out_shape)
-            if self.adapter:
-                out = self.adapter.apply(x=x, out=out)
-            return out
         check(
             lib.b2q_mm(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)), _ptr(self._zeros_dev),
                        _ptr(self.perm), _ptr(self._bias_for(x.dtype)), _ptr(out), M, K, N, self.bits,
@@ -423,6 +359,10 @@ class B200QuantLinear(nn.Module):
         M = x2.shape[0]
         if not (1 <= M <= DECODE_MAX_M) or self.bits != 4 or self.perm is not None or x.dtype not in _DTYPE_CODE:
             raise B2QError("forward_allreduce: decode tier only (bits=4, 1 <= tokens <= 8, no act-order, fp16/bf16)")
+        if self.adapter:
+            # the adapter's low-rank update belongs to the FULL layer output; applying it to one rank's partial sum (or
+            # dropping it silently) would change the result: callers use forward() + all-reduce instead
+            raise B2QError("forward_allreduce: modules with an adapter must use forward() followed by the all-reduce")
         out = torch.empty((M, N), dtype=x.dtype, device=x.device)
         check(
             lib.b2q_decode_allreduce(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)),
@@ -448,13 +388,6 @@ class B200QuantLinear(nn.Module):
         m.bias = mk(bias) if bias is not None else None
         m.post_init()
         return m
-
-    @classmethod
-    def validate_device(cls, device) -> None:
-        """Reference contract (qlinear/__init__.py validate_device): raise if the module cannot live on `device`."""
-        dev = torch.device(device) if not isinstance(device, torch.device) else device
-        if dev.type != "cuda":
-            raise NotImplementedError(f"{cls.__name__} supports CUDA devices only, got `{dev}`")
 
     @torch.no_grad()
     def dequantize_weight(self, num_itr: int = 1, chunk: int = 2048) -> torch.Tensor:
@@ -489,3 +422,91 @@ class B200QuantLinear(nn.Module):
     def extra_repr(self) -> str:
         return (f"in_features={self.in_features}, out_features={self.out_features}, bits={self.bits}, "
                 f"group_size={self.group_size}, desc_act={self.desc_act}, sym={self.sym}")
+
+
+class B200QuantLinear(B200KernelMixin, nn.Module):
+    """Stand-alone module (no import of the reference package)."""
+
+    # ---- capability declaration (names follow the reference's BaseQuantLinear) ----
+    SUPPORTS_BACKENDS = ["b200"]
+    SUPPORTS_METHODS = ["gptq"]
+    SUPPORTS_FORMATS = {"gptq": 120, "gptq_v2": 120}  # > TorchAten 110 (CPU) / Swordfish 101 / Machete 100 / Marlin 90
+    SUPPORTS_BITS = [4, 8]
+    SUPPORTS_GROUP_SIZE = [-1, 32, 64, 128]
+    SUPPORTS_DESC_ACT = [True, False]
+    SUPPORTS_SYM = [True, False]
+    SUPPORTS_SHARDS = True
+    SUPPORTS_TRAINING = False
+    SUPPORTS_AUTO_PADDING = False
+    SUPPORTS_IN_FEATURES_DIVISIBLE_BY = [64]
+    SUPPORTS_OUT_FEATURES_DIVISIBLE_BY = [32]
+    SUPPORTS_PACK_DTYPES = [torch.int32]
+    SUPPORTS_ADAPTERS = [Lora]  # gptqmodel_b200/adapter.py; any object with .apply(x=, out=) works, see forward()
+    SUPPORTS_DEVICES = ["cuda"]
+    SUPPORTS_PLATFORM = ["linux"]
+    SUPPORTS_DTYPES = [torch.float16, torch.bfloat16]
+    REQUIRES_FORMAT_V2 = True  # qzeros hold the true zero-point (loader adds 0x11111111 to v1 files)
+    QUANT_TYPE = "b200"
+
+    def __init__(
+        self,
+        bits: int,
+        group_size: int,
+        desc_act: bool,
+        sym: bool,
+        in_features: int,
+        out_features: int,
+        bias: bool = False,
+        pack_dtype: torch.dtype = torch.int32,
+        adapter=None,
+        register_buffers: bool = True,
+        **kwargs,
+    ):
+        nn.Module.__init__(self)
+        ok, err = self.validate(
+            bits=bits, group_size=group_size, desc_act=desc_act, sym=sym, in_features=in_features,
+            out_features=out_features, pack_dtype=pack_dtype, dtype=kwargs.get("dtype"),
+        )
+        if not ok:
+            raise err
+        self._b200_setup(bits, group_size, desc_act, sym, in_features, out_features, bias=bias, pack_dtype=pack_dtype,
+                         adapter=adapter, register_buffers=register_buffers, **kwargs)
+
+    # ---- validation -------------------------------------------------------------------------------
+    @classmethod
+    def validate_once(cls) -> Tuple[bool, Optional[Exception]]:
+        if not torch.cuda.is_available():
+            return False, NotImplementedError("B200QuantLinear needs a CUDA device")
+        major, minor = torch.cuda.get_device_capability()
+        if major != 10:
+            return False, NotImplementedError(f"B200QuantLinear is built for sm_100a only, found sm_{major}{minor}")
+        return True, None
+
+    @classmethod
+    def validate(cls, bits: int, group_size: int = -1, desc_act: bool = False, sym: bool = True,
+                 in_features: int = None, out_features: int = None, pack_dtype: torch.dtype = None,
+                 dtype: Optional[torch.dtype] = None, **_ignored) -> Tuple[bool, Optional[Exception]]:
+        """Static parameter check; NotImplementedError means "unsupported here, try the next kernel"."""
+        if bits not in cls.SUPPORTS_BITS:
+            return False, NotImplementedError(f"{cls.__name__}: bits={bits} not in {cls.SUPPORTS_BITS}")
+        if group_size not in cls.SUPPORTS_GROUP_SIZE:
+            return False, NotImplementedError(f"{cls.__name__}: group_size={group_size} not in {cls.SUPPORTS_GROUP_SIZE}")
+        if pack_dtype is not None and pack_dtype not in cls.SUPPORTS_PACK_DTYPES:
+            return False, NotImplementedError(f"{cls.__name__}: pack_dtype={pack_dtype} unsupported")
+        if dtype is not None and dtype not in cls.SUPPORTS_DTYPES:
+            return False, NotImplementedError(f"{cls.__name__}: dtype={dtype} unsupported")
+        if in_features is not None:
+            if in_features % 64 != 0:
+                return False, NotImplementedError(f"{cls.__name__}: in_features={in_features} must be divisible by 64")
+            if group_size != -1 and in_features % group_size != 0:
+                return False, NotImplementedError(f"{cls.__name__}: in_features % group_size != 0")
+        if out_features is not None and out_features % 32 != 0:
+            return False, NotImplementedError(f"{cls.__name__}: out_features={out_features} must be divisible by 32")
+        return True, None
+
+    @classmethod
+    def validate_device(cls, device) -> None:
+        """Reference contract (qlinear/__init__.py validate_device): raise if the module cannot live on `device`."""
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type != "cuda":
+            raise NotImplementedError(f"{cls.__name__} supports CUDA devices only, got `{dev}`")

@@ -226,7 +226,7 @@ class RowParallelLinear(torch.nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         tokens = x.numel() // x.shape[-1]
         if isinstance(self.reduce, FusedDecodeAllReduce) and 1 <= tokens <= 8 and getattr(self.inner, "perm", 1) is None \
-                and getattr(self.inner, "bits", 0) == 4:
+                and getattr(self.inner, "bits", 0) == 4 and not getattr(self.inner, "adapter", None):
             return self.inner.forward_allreduce(x, self.reduce)
         y = self.inner(x)
         if isinstance(self.reduce, P2PAllReduce) and y.numel() <= self.reduce.max_elems and y.numel() % 8 == 0:

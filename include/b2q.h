@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B2Q_ABI_VERSION 1
+#define B2Q_ABI_VERSION 2
 #define B2Q_DTYPE_F16 0
 #define B2Q_DTYPE_BF16 1
 
@@ -82,30 +82,16 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
              const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
              size_t workspace_bytes, void* stream);
 
-/* b2q_gemm with the STREAM-K work split of the CTA-pair tier (bits = 4, M > 128; b2q_gemm2s.cu): the last wave of
- * 256 x 256 output tiles is cut into equal k-block streams so that all SM pairs finish together (128 tiles on 74 pairs
- * otherwise run as 2 waves at 86 %).  sk_workspace: b2q_streamk_workspace_bytes() bytes of device memory, 16-byte
- * aligned, ZERO-FILLED ONCE by the caller and afterwards owned by the library (it parks fp32 partial tiles there and
- * re-arms its arrival counters itself); one workspace per stream.  Same results as b2q_gemm up to fp32 summation order.
- * EXPERIMENTAL in round 1: compiled, not yet validated on GPUs.
- * b2q_debug_gemm_plan (host only): plan5 = {tiles, pairs, k-blocks per tile, data-parallel tiles, stream-K tiles},
- * items = (tile, kb0, kb1, role) of CTA pair `pair` in processing order; role 0 whole tile, 1 + 16 * partials-awaited
- * owner of a split tile, 2 contributor; returns the item count, or -1 if it exceeds max_items. */
-size_t b2q_streamk_workspace_bytes(void);
-int b2q_gemm_streamk(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
-                     const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype,
-                     void* workspace, size_t workspace_bytes, void* sk_workspace, void* stream);
-int b2q_debug_gemm_plan(int M, int K, int N, int pair, int* plan5, int* items, int max_items);
-
 /* Sibling layers that consume the SAME activations (q/k/v, gate/up; module order in the reference:
  * gptqmodel/models/definitions/llama.py:17-27) in ONE decode launch: nsets <= 3 weight sets given as HOST arrays of
- * device pointers; all sets share M <= 8, K, bits = 4, group_size, dtype and symmetry (qzeros all NULL or all non-NULL),
- * no act-order.  out[i] is [M, N[i]].  Same arithmetic as nsets separate b2q_decode calls; results are bit-identical
+ * device pointers; all sets share M <= 8, K, bits = 4, group_size, dtype, symmetry (qzeros all NULL or all non-NULL) and
+ * the act-order permutation `perm` (NULL, or int32 [K] — q/k/v and gate/up of a GPTQ checkpoint are quantised against the
+ * same input Hessian and therefore carry the same g_idx).  out[i] is [M, N[i]].  Same arithmetic as nsets separate b2q_decode calls; results are bit-identical
  * whenever the fused launch cuts K like the single launches would (see b2q_debug_decode_plan), else they differ only
  * in the order the fp32 partial sums are added. */
 int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const void* const* scales,
-                     const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* N, int M, int K,
-                     int bits, int group_size, int dtype, void* stream);
+                     const int32_t* const* qzeros, const int32_t* perm, const void* const* bias, void* const* out,
+                     const int* N, int M, int K, int bits, int group_size, int dtype, void* stream);
 
 /* In-place all-reduce(sum) of a small 16-bit vector (n % 8 == 0, n <= max_elems) across `world` <= 8 GPUs of one
  * NVLink domain: the single collective of a row-parallel QuantLinear at decode time (the reference has

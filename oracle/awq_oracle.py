@@ -18,7 +18,7 @@ import torch
 AWQ_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]
 AWQ_REVERSE_ORDER = [0, 4, 1, 5, 2, 6, 3, 7]
 
-__all__ = ["awq_unpack", "awq_dequantize", "awq_forward", "awq_pack", "AWQ_ORDER", "AWQ_REVERSE_ORDER"]
+__all__ = ["awq_unpack", "awq_dequantize", "awq_forward", "awq_forward_exact", "awq_pack", "AWQ_ORDER", "AWQ_REVERSE_ORDER"]
 
 
 def awq_unpack(packed: torch.Tensor, bits: int = 4) -> torch.Tensor:
@@ -44,6 +44,24 @@ def awq_dequantize(qweight, qzeros, scales, group_size: int) -> torch.Tensor:
 def awq_forward(x, qweight, qzeros, scales, group_size: int, bias=None) -> torch.Tensor:
     W = awq_dequantize(qweight, qzeros, scales.to(x.dtype), group_size)
     y = (x.float() @ W.float()).to(x.dtype)  # fp32 accumulation, rounded once to the activation dtype
+    if bias is not None:
+        y = y + bias.to(x.dtype)
+    return y
+
+
+def awq_forward_exact(x, qweight, qzeros, scales, group_size: int, bias=None) -> torch.Tensor:
+    """The same layer in EXACT arithmetic: W = (q - z) * s WITHOUT the reference's per-weight rounding to 16 bits, the dot
+    product in float64, one rounding of the result to the activation dtype (then + bias like the reference).  Not what
+    the reference computes — it is what a kernel that applies the scale once per group to an exact integer dot product
+    (the decode / GEMV tiers) converges to; tests use it to separate kernel arithmetic errors from the reference's own
+    weight-rounding noise (tests/helpers.py::ref_rounding_slack)."""
+    q = awq_unpack(qweight).double()
+    z = awq_unpack(qzeros).double()
+    K = q.shape[0]
+    gs = group_size if group_size > 0 else K
+    g = torch.arange(K) // gs
+    W = (q - z[g]) * scales.to(x.dtype).double()[g]
+    y = (x.double() @ W).to(x.dtype)
     if bias is not None:
         y = y + bias.to(x.dtype)
     return y

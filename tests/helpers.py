@@ -77,15 +77,31 @@ def _record(what, rel, ratio):
         e["worst_err_over_tol"], e["worst_case"], e["rel"] = round(ratio, 4), what, rel
 
 
-def assert_close_rel(out, ref, rel=1e-3, what=""):
-    """|out - ref| <= rel * |ref| + rel * rms(ref): the north-star's "1e-3 rel fp16" with an absolute floor
-    for outputs that cancel to ~0."""
+def ref_rounding_slack(W, x, sigmas=4.0):
+    """Absolute deviation to be expected between an oracle that ROUNDS every dequantised weight to 16 bits (the
+    reference: W = dtype((q - z) * s), one rounding per weight, qlinear/__init__.py:1001-1003) and arithmetic that does
+    not (the decode / GEMV tiers apply the scale ONCE per group to an exact integer dot product — mathematically the
+    same sum, closer to exact arithmetic, but not the reference's rounding points).  Every weight carries an independent
+    relative rounding error uniform in +-2^-p (p = 11 for fp16, 8 for bf16): sigma = 2^-p / sqrt(3) per weight, so the two
+    results differ by a random sum with standard deviation sigma * sqrt(sum_k (W[k, n] * x[m, k])^2).  Returns `sigmas`
+    of those, [M, N].  tests/test_awq.py::test_scale_once_arithmetic_vs_per_weight_rounding shows on the reference's own
+    AWQ fixture that EXACT float64 arithmetic sits 1.18x outside the plain 1e-3 criterion for this reason alone."""
+    p = 11 if W.dtype == torch.float16 else 8
+    sigma = 2.0 ** -p / 3 ** 0.5
+    return sigmas * sigma * torch.sqrt((x.detach().float().cpu() ** 2) @ (W.detach().float().cpu() ** 2))
+
+
+def assert_close_rel(out, ref, rel=1e-3, what="", slack=None):
+    """|out - ref| <= rel * |ref| + rel * rms(ref) (+ slack): the north-star's "1e-3 rel fp16" with an absolute floor
+    for outputs that cancel to ~0.  `slack` ([M, N] or scalar, absolute): see ref_rounding_slack()."""
     o, r = out.detach().float().cpu(), ref.detach().float().cpu()
     assert o.shape == r.shape, (o.shape, r.shape)
     assert torch.isfinite(o).all(), f"{what}: non-finite output"
     rms = r.pow(2).mean().sqrt().item()
     err = (o - r).abs()
     tol = rel * r.abs() + rel * rms
+    if slack is not None:
+        tol = tol + slack
     bad = err > tol
     _record(what, rel, float((err / tol).max().item()) if err.numel() else 0.0)
     assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside {rel:g} rel; max abs err "

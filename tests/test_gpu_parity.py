@@ -364,6 +364,25 @@ def test_sibling_fusion_bit_identical(sym, gs, bias):
     assert not fuse_siblings([mods[0], other_k])
 
 
+def test_sibling_fusion_with_shared_act_order():
+    """q/k/v of a GPTQ act-order checkpoint share g_idx (same input Hessian): one decode launch gathers x[perm] once."""
+    from gptqmodel_b200 import fuse_siblings
+    K = 1024
+    Ls = [make_layer(K, n, group_size=128, sym=True, desc_act=True, seed=61) for n in (512, 256)]
+    assert torch.equal(Ls[0]["g_idx"], Ls[1]["g_idx"])
+    mods = [_module(L) for L in Ls]
+    assert mods[0].perm is not None and fuse_siblings(mods)
+    gen = torch.Generator().manual_seed(4)
+    for M in (1, 5):
+        x = (torch.randn(M, K, generator=gen) * 0.5).to(torch.float16)
+        for m, L in zip(mods, Ls):
+            assert_close_rel(m(x.to(DEV)), oracle_forward(L, x), 1e-3, f"act-order fused M={M}")
+    other = _module(make_layer(K, 256, group_size=128, sym=True, desc_act=True, seed=62))  # a different permutation
+    for m in mods:
+        m._siblings = None
+    assert not fuse_siblings([mods[0], other])
+
+
 @pytest.mark.parametrize("K,N,kind", [
     (8192, 1024, "q_proj column shard"), (1024, 8192, "o_proj row shard"),
     (8192, 3584, "gate/up column shard"), (3584, 8192, "down_proj row shard"),

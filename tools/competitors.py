@@ -122,10 +122,11 @@ class MarlinRef:
 
 def _scalar_type_id_u4b8():
     # core/scalar_type.hpp ScalarType::id(): bit-packed {exponent:8, mantissa:8, signed:1, bias:32, finite_values_only:1,
-    # nan_repr:8}; uint4b8 = ScalarType::uint(4, bias 8) -> exponent 0, mantissa 4, signed 0, bias 8
+    # nan_repr:8}; uint4b8 = ScalarType::uint(4, bias 8) -> exponent 0, mantissa 4, signed 0, bias 8, and the constructor's
+    # DEFAULT nan_repr = NAN_IEEE_754 (1) also for integer types (scalar_type.hpp:37-40)
     exponent, mantissa, signed, bias = 0, 4, 0, 8
     v, off = 0, 0
-    for val, width in ((exponent, 8), (mantissa, 8), (signed, 1), (bias, 32), (0, 1), (0, 8)):
+    for val, width in ((exponent, 8), (mantissa, 8), (signed, 1), (bias, 32), (0, 1), (1, 8)):
         v |= (val & ((1 << width) - 1)) << off
         off += width
     return v
