@@ -33,6 +33,11 @@ SYMBOLS = {
     "b2q_debug_set_trace": (None, [_vp]),
     "b2q_debug_decode_plan": (_i, [_i, _i, _i, _i, _i, _i, _vp]),
     "b2q_permute_cols": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "b2q_moe_align": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "b2q_moe_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b2q_moe_gate_up": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b2q_moe_down": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b2q_moe_combine": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
 
 

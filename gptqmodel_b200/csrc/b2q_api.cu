@@ -28,6 +28,11 @@ static EnvCfg read_env() {
   c.midm = env_int("B2Q_MIDM", 1);
   c.decode_blocks_m = env_int("B2Q_DECODE_BLOCKS_M", 0);
   c.decode_groups2 = env_int("B2Q_DECODE_GROUPS", 1) == 2;
+  c.decode_v2 = env_int("B2Q_DECODE_V2", -1);
+  c.decode2_gw = env_int("B2Q_DECODE2_GW", 0);
+  c.decode2_ks = env_int("B2Q_DECODE2_KS", 0);
+  c.decode2_xtma = env_int("B2Q_DECODE2_XTMA", 1);
+  c.decode2_fastsync = env_int("B2Q_DECODE2_FASTSYNC", 0);
   c.gemm2_persist = env_int("B2Q_GEMM2_PERSIST", 1);
   c.gemm2_dqw = env_int("B2Q_GEMM2_DQW", 8) == 4 ? 4 : 8;
   c.midm_ks = env_int("B2Q_MIDM_KS", 0);
@@ -357,6 +362,99 @@ int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t*
   if (M == 1 && bits == 8 && K % 128 == 0) return check_cuda(launch_gemv(a), "b2q_mm(gemv)");
   if (env().gemm_1cta) a.tune_ks = -1;
   return check_cuda(launch_gemm(a), "b2q_mm(gemm)");
+}
+
+// ---- grouped MoE expert path (b2q_moe.cu + the grouped modes of b2q_midm.cu) -----------------------------------------
+int b2q_moe_align(const int32_t* topk_ids, int T, int top_k, int E, int32_t* counts, int32_t* offsets,
+                  int32_t* sorted_pairs, void* stream) {
+  if (topk_ids == nullptr || counts == nullptr || offsets == nullptr || sorted_pairs == nullptr || T < 1 || top_k < 1 ||
+      E < 1) {
+    set_error("b2q_moe_align: bad argument (T=%d top_k=%d E=%d)", T, top_k, E);
+    return -2;
+  }
+  DeviceGuard dg(counts);
+  return check_cuda(launch_moe_align(topk_ids, T, top_k, E, counts, offsets, sorted_pairs, (cudaStream_t)stream),
+                    "b2q_moe_align");
+}
+
+int b2q_moe_gather(const void* x, const int32_t* sorted_pairs, void* xs, int rows, int top_k, int K, void* stream) {
+  if (x == nullptr || sorted_pairs == nullptr || xs == nullptr || rows < 1 || top_k < 1 || K < 8 || K % 8 != 0 ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(xs) & 15)) {
+    set_error("b2q_moe_gather: bad argument (rows=%d top_k=%d K=%d; K %% 8 == 0, 16-byte aligned)", rows, top_k, K);
+    return -2;
+  }
+  DeviceGuard dg(xs);
+  return check_cuda(launch_moe_gather(x, sorted_pairs, xs, rows, top_k, K, (cudaStream_t)stream), "b2q_moe_gather");
+}
+
+static int moe_check(const char* fn, const void* x, const void* packed, const void* scales, const int32_t* counts,
+                     const int32_t* offsets, int E, int rows, int K, int N, int bits, int group_size, int dtype) {
+  if (counts == nullptr || offsets == nullptr || E < 1 || rows < 1 || bits != 4) {
+    set_error("%s: bad argument (E=%d rows=%d bits=%d; the grouped path serves 4-bit experts)", fn, E, rows, bits);
+    return -2;
+  }
+  return validate(fn, x, packed, scales, x, rows, K, N, bits, group_size, dtype);
+}
+
+int b2q_moe_gate_up(const void* xs, const void* packed1, const void* scales1, const int32_t* qzeros1,
+                    const void* packed3, const void* scales3, const int32_t* qzeros3, void* h, const int32_t* counts,
+                    const int32_t* offsets, int E, int rows, int active, int K, int N, int bits, int group_size, int dtype,
+                    void* stream) {
+  int v = moe_check("b2q_moe_gate_up", xs, packed1, scales1, counts, offsets, E, rows, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (packed3 == nullptr || scales3 == nullptr || h == nullptr || ((qzeros1 != nullptr) != (qzeros3 != nullptr)) ||
+      (reinterpret_cast<uintptr_t>(h) & 15) || (reinterpret_cast<uintptr_t>(packed3) & 15)) {
+    set_error("b2q_moe_gate_up: w3 / h missing or misaligned, or w1 and w3 differ in symmetry");
+    return -2;
+  }
+  DeviceGuard dg(packed1);
+  MmArgs a = make_args(xs, packed1, scales1, qzeros1, nullptr, nullptr, h, rows, K, N, bits, group_size, dtype, nullptr,
+                       0, stream);
+  MoeGroupedArgs g = {};
+  g.counts = counts;
+  g.offsets = offsets;
+  g.packed3 = packed3;
+  g.scales3 = scales3;
+  g.qzeros3 = qzeros3;
+  g.E = E;
+  g.rows = rows;
+  g.active = active;
+  return check_cuda(launch_midm_grouped(1, a, g), "b2q_moe_gate_up");
+}
+
+int b2q_moe_down(const void* h, const void* packed2, const void* scales2, const int32_t* qzeros2, const int32_t* counts,
+                 const int32_t* offsets, const int32_t* sorted_pairs, const float* pair_weights, float* ypair, int E,
+                 int rows, int active, int K, int N, int bits, int group_size, int dtype, void* stream) {
+  int v = moe_check("b2q_moe_down", h, packed2, scales2, counts, offsets, E, rows, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (sorted_pairs == nullptr || pair_weights == nullptr || ypair == nullptr ||
+      (reinterpret_cast<uintptr_t>(ypair) & 15)) {
+    set_error("b2q_moe_down: sorted_pairs / pair_weights / ypair missing or misaligned");
+    return -2;
+  }
+  DeviceGuard dg(packed2);
+  MmArgs a = make_args(h, packed2, scales2, qzeros2, nullptr, nullptr, ypair, rows, K, N, bits, group_size, dtype, nullptr,
+                       0, stream);
+  MoeGroupedArgs g = {};
+  g.counts = counts;
+  g.offsets = offsets;
+  g.sorted_pairs = sorted_pairs;
+  g.pair_weights = pair_weights;
+  g.ypair = ypair;
+  g.E = E;
+  g.rows = rows;
+  g.active = active;
+  return check_cuda(launch_midm_grouped(2, a, g), "b2q_moe_down");
+}
+
+int b2q_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int dtype, void* stream) {
+  if (ypair == nullptr || y == nullptr || T < 1 || top_k < 1 || N < 4 || N % 4 != 0 || (dtype != 0 && dtype != 1) ||
+      (reinterpret_cast<uintptr_t>(ypair) & 15) || (reinterpret_cast<uintptr_t>(y) & 7)) {
+    set_error("b2q_moe_combine: bad argument (T=%d top_k=%d N=%d)", T, top_k, N);
+    return -2;
+  }
+  DeviceGuard dg(y);
+  return check_cuda(launch_moe_combine(ypair, y, T, top_k, N, dtype, (cudaStream_t)stream), "b2q_moe_combine");
 }
 
 }  // extern "C"

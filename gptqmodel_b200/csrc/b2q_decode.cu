@@ -19,8 +19,6 @@
 //  * act-order: rows sorted by group at prepack, the x[perm[k']] gather is fused into the activation staging.
 // Replaces the decode tiers of swordfish_mm (swordfish_mm.cu:216-286, mma.sync + cp.async + atomics) and Marlin's
 // small-M path (marlin_template.h) in the reference.
-#include <cstdlib>
-
 #include "b2q_common.cuh"
 #include "b2q_decode.cuh"
 #include "b2q_internal.h"
@@ -150,39 +148,57 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   stamp(2);
 
   // ---- 2. stage x[m, k-range] (act-order gather fused) + per-(64 k block, token) sums, ONCE ------
+  // A thread's loads (up to SX_UNROLL x 16 bytes, K = 14336 needs 3.5 per thread) are all issued BEFORE the first is
+  // consumed: the rolled loop paid one dependent L2 round trip per iteration (2.6 us of the 11 us down_proj launch,
+  // profiles/r02_decode_notes.md).
   {
     const int n8 = (q1 - q0) * 16;   // uint4 (8 halves) per token row in this CTA's k-range
     const int tot = M * n8;
     const int totr = (tot + 31) & ~31;
-    for (int i = threadIdx.x; i < totr; i += blockDim.x) {
-      uint4 xv = make_uint4(0, 0, 0, 0);
-      int m = 0, j = 0;
-      if (i < tot) {
-        m = i / n8;
-        j = i - m * n8;
-        const T* xr = x + (size_t)m * K;
-        if (PERM) {
-          const int4* pp = reinterpret_cast<const int4*>(perm + (size_t)q0 * 128) + 2 * j;
-          const int4 p0 = pp[0], p1 = pp[1];
-          const uint16_t* xu = reinterpret_cast<const uint16_t*>(xr);
-          xv.x = (uint32_t)xu[p0.x] | ((uint32_t)xu[p0.y] << 16);
-          xv.y = (uint32_t)xu[p0.z] | ((uint32_t)xu[p0.w] << 16);
-          xv.z = (uint32_t)xu[p1.x] | ((uint32_t)xu[p1.y] << 16);
-          xv.w = (uint32_t)xu[p1.z] | ((uint32_t)xu[p1.w] << 16);
-        } else {
-          xv = reinterpret_cast<const uint4*>(xr + (size_t)q0 * 128)[j];
+    constexpr int SX_UNROLL = 4;
+    auto f2 = [](uint32_t u) {
+      const T* h = reinterpret_cast<const T*>(&u);
+      return E::to_f(h[0]) + E::to_f(h[1]);
+    };
+    for (int i0 = threadIdx.x; i0 < totr; i0 += blockDim.x * SX_UNROLL) {
+      uint4 xv[SX_UNROLL];
+      int mm[SX_UNROLL], jj[SX_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SX_UNROLL; ++u) {
+        const int i = i0 + u * blockDim.x;
+        xv[u] = make_uint4(0, 0, 0, 0);
+        mm[u] = 0;
+        jj[u] = 0;
+        if (i < tot) {
+          const int m = i / n8, j = i - m * n8;
+          mm[u] = m;
+          jj[u] = j;
+          const T* xr = x + (size_t)m * K;
+          if (PERM) {
+            const int4* pp = reinterpret_cast<const int4*>(perm + (size_t)q0 * 128) + 2 * j;
+            const int4 p0 = pp[0], p1 = pp[1];
+            const uint16_t* xu = reinterpret_cast<const uint16_t*>(xr);
+            xv[u].x = (uint32_t)xu[p0.x] | ((uint32_t)xu[p0.y] << 16);
+            xv[u].y = (uint32_t)xu[p0.z] | ((uint32_t)xu[p0.w] << 16);
+            xv[u].z = (uint32_t)xu[p1.x] | ((uint32_t)xu[p1.y] << 16);
+            xv[u].w = (uint32_t)xu[p1.z] | ((uint32_t)xu[p1.w] << 16);
+          } else {
+            xv[u] = reinterpret_cast<const uint4*>(xr + (size_t)q0 * 128)[j];
+          }
         }
-        reinterpret_cast<uint4*>(sx + (size_t)m * kspan)[j] = xv;
       }
-      auto f2 = [](uint32_t u) {
-        const T* h = reinterpret_cast<const T*>(&u);
-        return E::to_f(h[0]) + E::to_f(h[1]);
-      };
-      float sm = (f2(xv.x) + f2(xv.y)) + (f2(xv.z) + f2(xv.w));
-      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-      sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-      if ((i & 7) == 0 && i < tot) xsum[(j >> 3) * 8 + m] = sm;  // 8 uint4 = one 64-k block
+#pragma unroll
+      for (int u = 0; u < SX_UNROLL; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < totr) {  // warp-uniform (totr and the strides are multiples of 32)
+          if (i < tot) reinterpret_cast<uint4*>(sx + (size_t)mm[u] * kspan)[jj[u]] = xv[u];
+          float sm = (f2(xv[u].x) + f2(xv[u].y)) + (f2(xv[u].z) + f2(xv[u].w));
+          sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+          sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+          sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+          if ((i & 7) == 0 && i < tot) xsum[(jj[u] >> 3) * 8 + mm[u]] = sm;  // 8 uint4 = one 64-k block
+        }
+      }
     }
     // zero the token columns >= M once (read by the fix-up of lanes whose columns are padding)
     for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
@@ -451,10 +467,21 @@ bool decode_supported(const MmArgs& a) {
 int launch_decode2_sets(const MmArgs& a, const DecSets& sets);  // b2q_decode2.cu (experimental), -2 = no configuration
 
 static int launch_decode_sets(const MmArgs& a, const DecSets& sets) {
+  // Kernel choice (same-box A/B of every Llama-3-8B launch shape, profiles/r02_decode_v1_v2_sweep.log): launches whose CTAs
+  // walk SEVERAL 32-feature tiles (more tiles than SMs: fused q|k|v 192, gate|up 896 tiles) run on decode2_kernel — warps
+  // park their partial sums and the CTA meets once, instead of a CTA barrier + reduction per tile (6.5 vs 8.5 us and
+  // 18.8 vs 19.9 us); single-tile launches (o_proj, down_proj: 128 tiles) keep decode_kernel, whose one reduction is
+  // cheaper (4.8 vs 5.5 us, 11.2 vs 12.5 us).  B2Q_DECODE_V2=1 / 0 forces one kernel for A/B runs.
   {
-    const char* v2 = getenv("B2Q_DECODE_V2");
-    if (v2 != nullptr && v2[0] == '1') {
-      const int rc = launch_decode2_sets(a, sets);
+    const int mode = env().decode_v2;  // -1 auto, 0 never, 1 always
+    const int NT = sets.tile_end[sets.nsets - 1];
+    if (mode == 1 || (mode < 0 && NT > 148 && a.tune_ks <= 0 && a.tune_warps <= 0)) {
+      MmArgs a2 = a;
+      if (mode < 0) {  // the configuration that won the sweep: no split-K, one 16-warp group
+        a2.tune_ks = 1;
+        a2.tune_warps = 16;
+      }
+      const int rc = launch_decode2_sets(a2, sets);
       if (rc != -2) return rc;
     }
   }

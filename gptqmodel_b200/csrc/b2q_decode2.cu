@@ -1,5 +1,6 @@
-// b2q_decode2.cu — second generation of the 4-bit decode tier (M <= 8).  EXPERIMENTAL: selected only with
-// B2Q_DECODE_V2=1 until it has passed the GPU parity suite (tests/test_gpu_parity.py, B2Q_TEST_V2=1).
+// b2q_decode2.cu — second generation of the 4-bit decode tier (M <= 8).  GPU-validated in round 2 (the whole parity suite
+// passes with it forced on: profiles/r02_ab_experimental.json) and selected per launch shape by launch_decode_sets
+// (b2q_decode.cu): multi-tile launches run here, single-tile launches on decode_kernel.
 //
 // Same data path as b2q_decode.cu (fragment-major T4 tiles -> per-warp cp.async.bulk ring -> mma.sync on raw
 // bias+q operands -> per-group fp32 fix-up, cluster split-K through distributed shared memory); what changes is
@@ -17,8 +18,6 @@
 //    of its OWN k-quads (the same quads in every tile), so no CTA barrier separates staging from the main loop.
 //    Act-order layers keep the gather loop of v1 (a gather cannot be a bulk copy).
 // Arithmetic per output element is the same as v1 except for the summation order of the fp32 partials.
-#include <cstdlib>
-
 #include "b2q_common.cuh"
 #include "b2q_decode.cuh"
 #include "b2q_internal.h"
@@ -466,17 +465,12 @@ static size_t decode2_smem(int M, int warps, int gw, int qpc, int max_tiles, int
          rows * gw * 32 * 4 + (ks > 1 ? rows * 32 * 4 : 0) + (size_t)warps * DEC_STAGES * 8 + 8 + 16;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
-}
-
 // Pick (split-K ranks, warps per CTA, warps per group) minimising the critical path in quads per warp.
 static bool decode2_config(const MmArgs& a, int NT, Decode2Cfg& best) {
   const int quads = a.K / 128;
   const int SMS = 148;
-  const int force_gw = env_int("B2Q_DECODE2_GW", 0);  // A/B switches for whole-model runs (bench.py --decode-v2)
-  const int force_ks = env_int("B2Q_DECODE2_KS", 0);
+  const int force_gw = env().decode2_gw;  // A/B switches (read once at load; b2q_debug_reload_env() re-reads them)
+  const int force_ks = env().decode2_ks;
   double best_cost = 1e30;
   bool found = false;
   for (int ks = 1; ks <= 8; ks *= 2) {
@@ -489,6 +483,7 @@ static bool decode2_config(const MmArgs& a, int NT, Decode2Cfg& best) {
       if (a.tune_warps > 0 && warps != a.tune_warps) continue;
       for (int gw = warps; gw >= 1; gw /= 2) {
         if (force_gw > 0 && gw != force_gw) continue;
+        if (force_gw <= 0 && a.tune_warps > 0 && a.tune_ks > 0 && gw != warps) continue;  // pinned plan: one group
         const int ngroups = warps / gw;
         int C = SMS / ks;
         if (C * ngroups > NT) C = (NT + ngroups - 1) / ngroups;
@@ -550,7 +545,7 @@ static int launch_decode2_t(const MmArgs& a, const DecSets& sets, const Decode2C
   int gsh = 31;  // per-channel: every k-block is group 0
   if (a.group_size == 64) gsh = 0;
   else if (a.group_size == 128) gsh = 1;
-  const int xtma = (env_int("B2Q_DECODE2_XTMA", 1) ? 1 : 0) | (env_int("B2Q_DECODE2_FASTSYNC", 0) ? 2 : 0);
+  const int xtma = (env().decode2_xtma ? 1 : 0) | (env().decode2_fastsync ? 2 : 0);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sets, a.perm, (const T*)a.x, a.M, a.K, gsh, c.qpc, c.max_tiles, c.gw,
                                      c.stl, xtma, ar, (unsigned long long*)g_trace_ptr);
   return (int)e;

@@ -50,6 +50,24 @@ int launch_gemm(const MmArgs& a);
 bool midm_supported(const MmArgs& a);
 int midm_ranks(int K, int N);
 int launch_midm(const MmArgs& a, const void* x);
+// grouped (MoE) launches of the small-batch tier; the routing tables live on the device (b2q_moe.cu builds them)
+struct MoeGroupedArgs {
+  const int32_t* counts;        // [E]
+  const int32_t* offsets;       // [E]
+  const int32_t* sorted_pairs;  // [rows]            (mode 2)
+  const float* pair_weights;    // [rows]            (mode 2)
+  const void* packed3;          // mode 1: second weight set (w3), stacked like the first
+  const void* scales3;
+  const void* qzeros3;
+  float* ypair;                 // mode 2: [rows, N] fp32
+  int E, rows, active;          // experts, (token, k) pairs, experts expected to be active (grid sizing only)
+};
+int launch_midm_grouped(int mode, const MmArgs& a, const MoeGroupedArgs& g);
+int launch_moe_align(const int32_t* topk_ids, int T, int top_k, int E, int32_t* counts, int32_t* offsets,
+                     int32_t* sorted_pairs, cudaStream_t stream);
+int launch_moe_gather(const void* x, const int32_t* sorted_pairs, void* xs, int rows, int top_k, int K,
+                      cudaStream_t stream);
+int launch_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int dtype, cudaStream_t stream);
 int launch_gemm2(const MmArgs& a, const void* x);
 int gemm_gshc(const MmArgs& a);  // 4-bit, CTA-pair (cta_group::2) tier; x already permuted
 int launch_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs,
@@ -64,6 +82,11 @@ struct EnvCfg {
   int midm;             // B2Q_MIDM=0           : M <= 128 on the padded single-CTA tier (round-1 path) instead of b2q_midm.cu
   int decode_blocks_m;  // B2Q_DECODE_BLOCKS_M=n: 9 <= M <= n served by passes of the decode tier over 8-row blocks (default 0)
   int decode_groups2;   // B2Q_DECODE_GROUPS=2
+  int decode_v2;        // B2Q_DECODE_V2=1 / 0  : force decode2_kernel / decode_kernel (default -1: per launch shape)
+  int decode2_gw;       // B2Q_DECODE2_GW=n     : force warps per tile group of decode2_kernel
+  int decode2_ks;       // B2Q_DECODE2_KS=n     : force its split-K cluster size
+  int decode2_xtma;     // B2Q_DECODE2_XTMA=0   : LDG staging instead of the bulk-copied activations
+  int decode2_fastsync; // B2Q_DECODE2_FASTSYNC=1: CTA-fenced cluster barriers
   int gemm2_persist;    // B2Q_GEMM2_PERSIST=0  : one tile per CTA pair
   int gemm2_dqw;        // B2Q_GEMM2_DQW=4
   int midm_ks;          // B2Q_MIDM_KS=n        : force the split-K cluster size of the small-batch tier

@@ -38,8 +38,26 @@ constexpr int MM_THREADS = 64 + MM_DQ_THREADS;
 // cost ~0.39 us = one HBM round trip / 4 (profiles/r02_midm_v1_bench.log: 25 us for the 64 k-blocks of 4096 x 4096 on one
 // CTA per tile); Little's law asks for ~43 KB per SM at 6.5 TB/s.  The DEQUANTISED ring (WST stages of 16 KB) only
 // decouples the dequant warps from the tensor core.
-template <int BITS, int NTOK, int PST, int WST>
+// MODE 0: one QuantLinear.  MODE 1 / 2: GROUPED over the experts of a MoE block (b2q_moe.cu): blockIdx.z = (expert, token
+// block); the rows of an expert are contiguous in the expert-sorted activation matrix; CTAs beyond an expert's row count
+// exit at once.  MODE 1 runs TWO weight sets (w1 = gate, w3 = up) through the pipeline back to back into two TMEM
+// accumulators and stores silu(gate) * up; MODE 2 (w2 = down) scales each row by its routing weight and scatters it to the
+// row's (token, k) slot of an fp32 buffer.
+struct MoeArgs {
+  const int32_t* counts;        // [E] rows of expert e
+  const int32_t* offsets;       // [E] first row of expert e in the sorted order
+  const int32_t* sorted_pairs;  // [rows] pair index (token * top_k + j) of sorted row i            (MODE 2)
+  const float* pair_weights;    // [rows] routing weight, indexed by PAIR index                      (MODE 2)
+  const uint4* packed3;         // second weight set, same shapes / strides as the first             (MODE 1)
+  const void* scales3;
+  const uint32_t* qzeros3;
+  float* ypair;                 // [rows, N] fp32, row = pair index                                   (MODE 2)
+  int tblocks;                  // token blocks (of NTOK rows) per expert in gridDim.z
+};
+
+template <int BITS, int NTOK, int PST, int WST, int MODE = 0>
 struct MidCfg {
+  static constexpr int NSETS = MODE == 1 ? 2 : 1;
   static constexpr int SUB = BITS / 4;
   static constexpr int W_BYTES = MM_BF * MM_BK * 2;      // dequantised weights, A operand: 16 KB
   static constexpr int X_BYTES = NTOK * MM_BK * 2;       // activations, B operand (first in its stage: 1024-B aligned)
@@ -48,8 +66,9 @@ struct MidCfg {
   static constexpr int PSTAGE_BYTES = X_BYTES + P_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = WST * W_BYTES + PST * PSTAGE_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = NTOK < 32 ? 32 : NTOK;
-  static constexpr int PART_BYTES = NTOK * MM_BF * 4;    // fp32 partial tile [token][feature]
+  static constexpr int TMEM_COLS = NSETS * NTOK < 32 ? 32 : NSETS * NTOK;
+  static constexpr int PART_BYTES = NSETS * NTOK * MM_BF * 4;  // fp32 partial tile(s) [set][token][feature]
+  static_assert(MODE == 0 || BITS == 4, "the grouped (MoE) modes are built for 4-bit experts");
   static_assert(PSTAGE_BYTES % 1024 == 0, "x tiles must stay 1024-byte aligned (SWIZZLE_128B atoms)");
   static_assert(PART_BYTES <= WST * W_BYTES + PST * PSTAGE_BYTES, "the fp32 partial tile reuses the idle stage buffers");
   static_assert((3 * PST + 2 * WST + 1) * 8 + 16 <= BAR_BYTES, "mbarrier area");
@@ -64,13 +83,37 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST>
+template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST, int MODE, int DQG>
 __global__ void __launch_bounds__(MM_THREADS, 1)
     midm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
                 const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, const T* __restrict__ bias,
-                T* __restrict__ out, int M, int K, int N, int gshc, int kpc) {
-  using C = MidCfg<BITS, NTOK, PST, WST>;
+                T* __restrict__ out, int M, int K, int N, int gshc, int kpc, const __grid_constant__ MoeArgs G) {
+  using C = MidCfg<BITS, NTOK, PST, WST, MODE>;
   using E = ET<T>;
+  constexpr int NSETS = C::NSETS;
+  int row0 = 0;  // first row of this CTA's token block in the activation matrix
+  const uint4* packed_b = nullptr;
+  const T* scales_b = nullptr;
+  const uint32_t* qzeros_b = nullptr;
+  if (MODE != 0) {
+    // the routing tables are written by the preceding kernel of the stream: nothing may be read before it has finished
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int e = (int)blockIdx.z / G.tblocks, tb = (int)blockIdx.z - e * G.tblocks;
+    const int cnt = G.counts[e];
+    if (tb * NTOK >= cnt) return;  // same decision in every CTA of the cluster (they differ in blockIdx.y only)
+    row0 = G.offsets[e] + tb * NTOK;
+    M = min(NTOK, cnt - tb * NTOK);
+    const size_t groups = (size_t)(K >> 5) >> gshc;  // quantisation groups along K (gshc = log2(32-k chunks per group))
+    const size_t wstride = (size_t)K * N / 32, sstride = (gshc >= 31 ? 1 : groups) * (size_t)N;
+    packed += (size_t)e * wstride;
+    scales += (size_t)e * sstride;
+    if (ASYM) qzeros += (size_t)e * (sstride >> 3);
+    if (MODE == 1) {
+      packed_b = G.packed3 + (size_t)e * wstride;
+      scales_b = reinterpret_cast<const T*>(G.scales3) + (size_t)e * sstride;
+      if (ASYM) qzeros_b = G.qzeros3 + (size_t)e * (sstride >> 3);
+    }
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -93,6 +136,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
   const uint32_t nrank = cluster_nctarank(), crank = cluster_ctarank();
   const int kb0 = (int)crank * kpc, kb1 = min(K / MM_BK, kb0 + kpc);
   const int nkb = kb1 - kb0;
+  const int NI = NSETS * nkb;  // pipeline iterations: the k-blocks of set 0, then (MODE 1) of set 1
 
   // PDL: the next kernel in the stream may start its own prologue / weight prefetch now
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -102,10 +146,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     for (int s = 0; s < PST; ++s) {
       mbar_init(bar_pfull + 8 * s, 1);
       mbar_init(bar_xfull + 8 * s, 1);
-      mbar_init(bar_pempty + 8 * s, MM_DQ_THREADS + 1);  // every dequant thread has read the codes + the MMA has read x
+      mbar_init(bar_pempty + 8 * s, MM_DQ_THREADS / DQG + 1);  // the block's dequant group has read the codes + the MMA x
     }
     for (int s = 0; s < WST; ++s) {
-      mbar_init(bar_wready + 8 * s, MM_DQ_THREADS);
+      mbar_init(bar_wready + 8 * s, MM_DQ_THREADS / DQG);
       mbar_init(bar_wempty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
@@ -127,146 +171,193 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
       const uint32_t pbytes4 = (uint32_t)min(8, FT - ft0) * 512u;
       const uint32_t pbytes8 = (uint32_t)ntiles * C::SUB * 512u;
       const uint32_t sbytes = (uint32_t)min(MM_BF, N - n0) * 2u, zbytes = ASYM ? sbytes / 4u : 0u;
-      auto load_weights = [&](int kb, int s) {
+      auto load_weights = [&](int i, int s) {
+        const bool second = NSETS > 1 && i >= nkb;
+        const int kb = kb0 + (second ? i - nkb : i);
+        const uint4* pk = second ? packed_b : packed;
+        const T* sc = second ? scales_b : scales;
+        const uint32_t* zq = second ? qzeros_b : qzeros;
         if (BITS == 4) {
           // the scale / zero rows of the block's group(s) travel with the packed codes (no LDG in the dequant warps)
           const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
           const int nrows = (g1 != g0) ? 2 : 1;
           mbar_expect_tx(bar_pfull + 8 * s, pbytes4 + nrows * (sbytes + zbytes));
-          bulk_load(sPs(s), packed + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_pfull + 8 * s);
+          bulk_load(sPs(s), pk + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_pfull + 8 * s);
           for (int r = 0; r < nrows; ++r) {
             const int gr = r ? g1 : g0;
-            bulk_load(sPs(s) + 4096 + r * 320, scales + (size_t)gr * N + n0, sbytes, bar_pfull + 8 * s);
+            bulk_load(sPs(s) + 4096 + r * 320, sc + (size_t)gr * N + n0, sbytes, bar_pfull + 8 * s);
             if (ASYM)
-              bulk_load(sPs(s) + 4096 + r * 320 + 256, qzeros + (size_t)gr * (N >> 3) + (n0 >> 3), zbytes,
+              bulk_load(sPs(s) + 4096 + r * 320 + 256, zq + (size_t)gr * (N >> 3) + (n0 >> 3), zbytes,
                         bar_pfull + 8 * s);
           }
         } else {
           mbar_expect_tx(bar_pfull + 8 * s, 2 * pbytes8);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            bulk_load(sPs(s) + j * C::P_CHUNK_BYTES, packed + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes8,
+            bulk_load(sPs(s) + j * C::P_CHUNK_BYTES, pk + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes8,
                       bar_pfull + 8 * s);
         }
       };
-      auto load_x = [&](int kb, int s) {
+      auto load_x = [&](int i, int s) {
+        const int kb = kb0 + ((NSETS > 1 && i >= nkb) ? i - nkb : i);
         mbar_expect_tx(bar_xfull + 8 * s, C::X_BYTES);
-        tma_load_2d(sXs(s), &tmap_x, bar_xfull + 8 * s, kb * MM_BK, 0);
+        tma_load_2d(sXs(s), &tmap_x, bar_xfull + 8 * s, kb * MM_BK, row0);
       };
       // weights never depend on the previous kernel: the first PST blocks stream (and are dequantised) before the
-      // producer of x has finished
-      const int pre = min(PST, nkb);
-      for (int i = 0; i < pre; ++i) load_weights(kb0 + i, i);
+      // producer of x has finished (MODE 0; the grouped modes had to wait for the routing tables at the very top)
+      const int pre = min(PST, NI);
+      for (int i = 0; i < pre; ++i) load_weights(i, i);
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (int i = 0; i < pre; ++i) load_x(kb0 + i, i);
-      for (int i = pre; i < nkb; ++i) {
+      for (int i = 0; i < pre; ++i) load_x(i, i);
+      for (int i = pre; i < NI; ++i) {
         const int s = i % PST;
         mbar_wait(bar_pempty + 8 * s, ((i / PST) & 1) ^ 1);
-        load_weights(kb0 + i, s);
-        load_x(kb0 + i, s);
+        load_weights(i, s);
+        load_x(i, s);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = umma_idesc_f16(E::FMT, MM_BF, NTOK);
-    for (int i = 0; i < nkb; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int s = i % PST, ws = i % WST;
       mbar_wait(bar_xfull + 8 * s, (i / PST) & 1);
       mbar_wait(bar_wready + 8 * ws, (i / WST) & 1);
       tc_fence_after();
       if (lane == 0) {
+        const bool second = NSETS > 1 && i >= nkb;
+        const uint32_t dcol = tbase + (second ? NTOK : 0);          // set 1 accumulates in the next NTOK TMEM columns
+        const int first = second ? nkb : 0;                         // first iteration of this set: overwrite
         const uint64_t wdesc = umma_desc_k_sw128(sW + ws * C::W_BYTES);
         const uint64_t xdesc = umma_desc_k_sw128(sXs(s));
 #pragma unroll
-        for (int k = 0; k < MM_BK / 16; ++k) umma_f16(tbase, wdesc + 2 * k, xdesc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < MM_BK / 16; ++k)
+          umma_f16(dcol, wdesc + 2 * k, xdesc + 2 * k, idesc, (i != first || k != 0) ? 1u : 0u);
         umma_commit(bar_wempty + 8 * ws);  // the dequantised stage may be overwritten
         umma_commit(bar_pempty + 8 * s);   // the x tile of the packed stage has been read
-        if (i == nkb - 1) umma_commit(bar_tfull);
+        if (i == NI - 1) umma_commit(bar_tfull);
       }
       __syncwarp();
     }
   } else {
     // ================================ dequant warps ================================
+    // The dequant warps form DQG groups of TG threads; group gq takes the pipeline iterations i = gq, gq + DQG, ...  One
+    // iteration is a serial chain of latencies for a warp (mbarrier wake-up, LDS, ~75 ALU instructions per uint4, STS,
+    // fence.proxy.async, arrive: ~800 clk) — with all eight warps on the SAME k-block (first version) that chain WAS the
+    // k-block time (0.43 us per k-block at any ring depth, profiles/r02_midm_notes.md); with DQG blocks in flight the
+    // chains overlap and the tier becomes issue-bound instead.
     const int t = threadIdx.x - 64;  // 0..255
+    constexpr int TG = MM_DQ_THREADS / DQG;
+    const int gq = t / TG, tl = t - gq * TG;
     constexpr int PF = 32 / BITS;
     constexpr int ZSYM = 1 << (BITS - 1);
     if (BITS == 4) {
-      // one fragment-major uint4 per thread and stage: feature tile t>>5 (16 features), lane' = t&31 = 4g+tt
-      const int lp = t & 31, g = lp >> 2, tt = lp & 3;
-      const int f_lo = (t >> 5) * 16 + g, f_hi = f_lo + 8;
-      for (int i = 0; i < nkb; ++i) {
-        const int kb = kb0 + i, s = i % PST, ws = i % WST;
+      // DQG fragment-major uint4 per thread and iteration: q = tl + TG*u -> feature tile q>>5 (16 features), lane' = q&31
+      constexpr int U = DQG;
+      const int lp = tl & 31, g = lp >> 2, tt = lp & 3;
+      for (int i = gq; i < NI; i += DQG) {
+        const int kb = kb0 + ((NSETS > 1 && i >= nkb) ? i - nkb : i), s = i % PST, ws = i % WST;
         mbar_wait(bar_pfull + 8 * s, (i / PST) & 1);
         const uint8_t* pst = smem + (sPs(s) - smem_base);
-        const uint4 pv = reinterpret_cast<const uint4*>(pst)[t];
         // this lane's 16 k of block kb lie in 32-k chunk 2*kb + (tt>>1)
         const int grow = ((2 * kb + (tt >> 1)) >> gshc) - ((2 * kb) >> gshc);  // 0 or 1
         const uint8_t* srow = pst + 4096 + grow * 320;
-        const uint32_t s_lo = *reinterpret_cast<const uint16_t*>(srow + f_lo * 2);
-        const uint32_t s_hi = *reinterpret_cast<const uint16_t*>(srow + f_hi * 2);
-        int zl = ZSYM, zh = ZSYM;
-        if (ASYM) {
-          const uint32_t zwl = *reinterpret_cast<const uint32_t*>(srow + 256 + (f_lo >> 3) * 4);
-          const uint32_t zwh = *reinterpret_cast<const uint32_t*>(srow + 256 + (f_hi >> 3) * 4);
-          zl = (int)((zwl >> (4 * g)) & 15u);  // feature % 8 == g for both rows
-          zh = (int)((zwh >> (4 * g)) & 15u);
+        uint4 pv[U];
+        uint32_t s_lo[U], s_hi[U];
+        int zl[U], zh[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int q = tl + TG * u;
+          const int f_lo = (q >> 5) * 16 + g, f_hi = f_lo + 8;
+          pv[u] = reinterpret_cast<const uint4*>(pst)[q];
+          s_lo[u] = *reinterpret_cast<const uint16_t*>(srow + f_lo * 2);
+          s_hi[u] = *reinterpret_cast<const uint16_t*>(srow + f_hi * 2);
+          zl[u] = zh[u] = ZSYM;
+          if (ASYM) {
+            const uint32_t zwl = *reinterpret_cast<const uint32_t*>(srow + 256 + (f_lo >> 3) * 4);
+            const uint32_t zwh = *reinterpret_cast<const uint32_t*>(srow + 256 + (f_hi >> 3) * 4);
+            zl[u] = (int)((zwl >> (4 * g)) & 15u);  // feature % 8 == g for both rows
+            zh[u] = (int)((zwh >> (4 * g)) & 15u);
+          }
         }
         mbar_arrive(bar_pempty + 8 * s);  // codes + scales are in registers: the producer may refill the packed stage
-        uint4 lo[2], hi[2];
-        Dequant<T, 4>::run(pv, s_lo, zl, s_hi, zh, lo, hi);
         if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);  // the MMA of block i - WST has read the stage
-        const uint32_t rlo = sW + ws * C::W_BYTES + f_lo * 128;
-        const uint32_t rhi = rlo + 8 * 128;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t off = (((uint32_t)(2 * tt + c)) ^ (uint32_t)g) << 4;  // (row & 7) == g for rows f and f+8
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rlo + off), "r"(lo[c].x), "r"(lo[c].y),
-                       "r"(lo[c].z), "r"(lo[c].w)
-                       : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rhi + off), "r"(hi[c].x), "r"(hi[c].y),
-                       "r"(hi[c].z), "r"(hi[c].w)
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_wready + 8 * ws);
-      }
-    } else {
-      // 8-bit: thread = (feature row fr, 32-k half j of the block); two uint4 (16 k each) per stage
-      const int fr = t & 127, j = t >> 7;
-      const int n = n0 + fr;
-      const int nsafe = (n < N) ? n : 0;
-      const int ntl = fr >> 5;
-      SZRaw cur = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb0 + j) >> gshc, nsafe, N), nxt = cur;
-      const uint32_t sw = (uint32_t)(fr & 7);
-      for (int i = 0; i < nkb; ++i) {
-        const int kb = kb0 + i, s = i % PST, ws = i % WST;
-        if (i + 1 < nkb) nxt = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + 2 + j) >> gshc, nsafe, N);
-        mbar_wait(bar_pfull + 8 * s, (i / PST) & 1);
-        const uint32_t brow = sW + ws * C::W_BYTES + fr * 128;
-        int z = ZSYM;
-        if (ASYM) z = (int)((cur.zw >> (BITS * (nsafe % PF))) & ((1u << BITS) - 1));
-        const uint4* pj = reinterpret_cast<const uint4*>(smem + (sPs(s) - smem_base) + j * C::P_CHUNK_BYTES);
-        uint4 pvs[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) pvs[h] = pj[(ntl * 2 + h) * 32 + lane];
-        mbar_arrive(bar_pempty + 8 * s);  // codes are in registers: the producer may refill the packed stage
-        if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint4 pv = pvs[h];
-          uint4 o[2];
-          Dequant<T, 8>::run(pv, cur.s, z, o);
+        for (int u = 0; u < U; ++u) {
+          const int q = tl + TG * u;
+          const int f_lo = (q >> 5) * 16 + g;
+          uint4 lo[2], hi[2];
+          Dequant<T, 4>::run(pv[u], s_lo[u], zl[u], s_hi[u], zh[u], lo, hi);
+          const uint32_t rlo = sW + ws * C::W_BYTES + f_lo * 128;
+          const uint32_t rhi = rlo + 8 * 128;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const uint32_t addr = brow + (((uint32_t)(j * 4 + h * 2 + c) ^ sw) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[c].x), "r"(o[c].y), "r"(o[c].z),
-                         "r"(o[c].w)
+            const uint32_t off = (((uint32_t)(2 * tt + c)) ^ (uint32_t)g) << 4;  // (row & 7) == g for rows f and f+8
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rlo + off), "r"(lo[c].x), "r"(lo[c].y),
+                         "r"(lo[c].z), "r"(lo[c].w)
+                         : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rhi + off), "r"(hi[c].x), "r"(hi[c].y),
+                         "r"(hi[c].z), "r"(hi[c].w)
                          : "memory");
           }
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_wready + 8 * ws);
-        cur = nxt;
+      }
+    } else {
+      // 8-bit: a group covers the 128 feature rows x two 32-k halves of a block: thread -> rows tl + TG*r, both halves,
+      // two uint4 (16 k each) per (row, half)
+      constexpr int R = 128 / TG;
+      for (int i = gq; i < NI; i += DQG) {
+        const int kb = kb0 + i, s = i % PST, ws = i % WST;
+        SZRaw sz[R][2];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int n = n0 + tl + TG * r;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) sz[r][j] = load_sz<T, BITS, ASYM>(scales, qzeros, (2 * kb + j) >> gshc, n < N ? n : 0, N);
+        }
+        mbar_wait(bar_pfull + 8 * s, (i / PST) & 1);
+        uint4 pvs[R][2][2];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int fr = tl + TG * r;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4* pj = reinterpret_cast<const uint4*>(smem + (sPs(s) - smem_base) + j * C::P_CHUNK_BYTES);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) pvs[r][j][h] = pj[((fr >> 5) * 2 + h) * 32 + (fr & 31)];
+          }
+        }
+        mbar_arrive(bar_pempty + 8 * s);  // codes are in registers: the producer may refill the packed stage
+        if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int fr = tl + TG * r;
+          const int n = n0 + fr;
+          const int nsafe = n < N ? n : 0;
+          const uint32_t brow = sW + ws * C::W_BYTES + fr * 128;
+          const uint32_t sw = (uint32_t)(fr & 7);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            int z = ZSYM;
+            if (ASYM) z = (int)((sz[r][j].zw >> (BITS * (nsafe % PF))) & ((1u << BITS) - 1));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint4 o[2];
+              Dequant<T, 8>::run(pvs[r][j][h], sz[r][j].s, z, o);
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const uint32_t addr = brow + (((uint32_t)(j * 4 + h * 2 + c) ^ sw) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[c].x), "r"(o[c].y), "r"(o[c].z),
+                             "r"(o[c].w)
+                             : "memory");
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_wready + 8 * ws);
       }
     }
 
@@ -277,7 +368,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     asm volatile("griddepcontrol.wait;" ::: "memory");  // (already satisfied) orders the global stores below
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;       // two warps share a quarter: they split the 16-token column chunks
-    for (int c = half; c < NTOK / 16; c += 2) {
+    // column chunk c of 16 tokens; with two weight sets the chunks NTOK/16 .. 2*NTOK/16-1 are set 1 (TMEM columns and
+    // partial-tile rows continue seamlessly: part[set * NTOK + token][feature])
+    for (int c = half; c < NSETS * NTOK / 16; c += 2) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
       tmem_ld_wait();
@@ -301,7 +394,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     if (nc < N) {
       for (int tok = (int)crank + (int)nrank * (t >> 5); tok < M; tok += (int)nrank * MM_DQ_WARPS) {
         const uint32_t local = sW + (uint32_t)tok * (MM_BF * 4) + (uint32_t)chunk * 16;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
         for (uint32_t r = 0; r < nrank; ++r) {
           uint32_t ra;
           float4 v;
@@ -314,14 +407,49 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
           acc[1] += v.y;
           acc[2] += v.z;
           acc[3] += v.w;
+          if (MODE == 1) {
+            asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(ra + (uint32_t)NTOK * (MM_BF * 4))
+                         : "memory");
+            acc2[0] += v.x;
+            acc2[1] += v.y;
+            acc2[2] += v.z;
+            acc2[3] += v.w;
+          }
         }
-        if (bias != nullptr) {
-          // reference order: round the matmul to the output dtype, then add bias (torch.py:337-342)
+        if (MODE == 0) {
+          if (bias != nullptr) {
+            // reference order: round the matmul to the output dtype, then add bias (torch.py:337-342)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] = E::to_f(E::from_f(acc[i])) + E::to_f(bias[nc + i]);
+            for (int i = 0; i < 4; ++i) acc[i] = E::to_f(E::from_f(acc[i])) + E::to_f(bias[nc + i]);
+          }
+          *reinterpret_cast<uint2*>(out + (size_t)tok * N + nc) =
+              make_uint2(E::pack2(acc[0], acc[1]), E::pack2(acc[2], acc[3]));
+        } else if (MODE == 1) {
+          // the per-expert module loop of the reference model rounds at every module boundary
+          // (act_fn(w1(x)) * w3(x) with 16-bit tensors): g = T(x W1), a = T(silu(g)), u = T(x W3), h = T(a * u)
+          float hv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float gq = E::to_f(E::from_f(acc[i])), uq = E::to_f(E::from_f(acc2[i]));
+            const float aq = E::to_f(E::from_f(gq / (1.f + __expf(-gq))));
+            hv[i] = aq * uq;
+          }
+          *reinterpret_cast<uint2*>(out + (size_t)(row0 + tok) * N + nc) =
+              make_uint2(E::pack2(hv[0], hv[1]), E::pack2(hv[2], hv[3]));
+        } else {
+          // y = T(h W2) like the module, then the routing weight; kept in fp32 in the row's (token, k) slot — the k slots
+          // of a token are summed (and rounded ONCE) by moe_combine_kernel: no atomics, deterministic
+          const int pair = G.sorted_pairs[row0 + tok];
+          const float w = G.pair_weights[pair];
+          float4 o;
+          o.x = w * E::to_f(E::from_f(acc[0]));
+          o.y = w * E::to_f(E::from_f(acc[1]));
+          o.z = w * E::to_f(E::from_f(acc[2]));
+          o.w = w * E::to_f(E::from_f(acc[3]));
+          *reinterpret_cast<float4*>(G.ypair + (size_t)pair * N + nc) = o;
         }
-        *reinterpret_cast<uint2*>(out + (size_t)tok * N + nc) =
-            make_uint2(E::pack2(acc[0], acc[1]), E::pack2(acc[2], acc[3]));
       }
     }
   }
@@ -346,22 +474,21 @@ int midm_ranks(int K, int N) {
   return ks;
 }
 
-template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST>
-static int launch_midm_t(const MmArgs& a, const void* x, int ks) {
-  using C = MidCfg<BITS, NTOK, PST, WST>;
+constexpr int MM_DQG = 4;  // dequant groups = k-blocks dequantised concurrently
+
+template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST, int MODE = 0>
+static int launch_midm_t(const MmArgs& a, const void* x, int ks, const MoeArgs& G = MoeArgs{}, int x_rows = 0,
+                         int grid_z = 1) {
+  using C = MidCfg<BITS, NTOK, PST, WST, MODE>;
   CUtensorMap tmap;
-  if (make_x_tmap_box(&tmap, x, a.M, a.K, a.dtype, NTOK) != 0) return -1;
-  auto kern = midm_kernel<T, BITS, ASYM, NTOK, PST, WST>;
-  // the attribute is per device (a process may serve several GPUs): setting it is cheap, do it on every launch
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  if (e != cudaSuccess) {
-    set_error("b2q_midm: cannot opt in to %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
-    return (int)e;
-  }
+  if (make_x_tmap_box(&tmap, x, MODE == 0 ? a.M : x_rows, a.K, a.dtype, NTOK) != 0) return -1;
+  auto kern = midm_kernel<T, BITS, ASYM, NTOK, PST, WST, MODE, MM_DQG>;
+  static uint32_t smem_ok = 0;  // per-device bit mask (a process may drive several GPUs)
+  if (int e = ensure_dyn_smem(kern, C::SMEM_BYTES, smem_ok, "b2q_midm")) return e;
   const int nkb = a.K / MM_BK;
   const int kpc = (nkb + ks - 1) / ks;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((a.N + MM_BF - 1) / MM_BF, ks, 1);
+  cfg.gridDim = dim3((a.N + MM_BF - 1) / MM_BF, ks, grid_z);
   cfg.blockDim = dim3(MM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = a.stream;
@@ -376,7 +503,7 @@ static int launch_midm_t(const MmArgs& a, const void* x, int ks) {
   cfg.numAttrs = a.pdl ? 2 : 1;
   return (int)cudaLaunchKernelEx(&cfg, kern, tmap, (const uint4*)a.packed, (const T*)a.scales,
                                  (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M, a.K, a.N, gemm_gshc(a),
-                                 kpc);
+                                 kpc, G);
 }
 
 bool midm_supported(const MmArgs& a) { return a.M >= 1 && a.M <= 128 && a.K % MM_BK == 0 && a.N % 32 == 0; }
@@ -388,20 +515,68 @@ int launch_midm(const MmArgs& a, const void* x) {
   const int nkb = a.K / MM_BK;
   while (ks > 1 && (ks - 1) * ((nkb + ks - 1) / ks) >= nkb) ks >>= 1;  // every rank needs at least one k-block
   const bool asym = a.qzeros != nullptr;
-  // ring depths: M <= 32 keeps the CTA under ~111 KB of shared memory so that the NEXT kernel's CTAs (programmatic
-  // dependent launch) become resident — and stream their first weights — while this kernel still runs; wider token boxes
-  // take the whole SM and go deeper instead
+  // ring depths: WST = 6 dequantised stages (4 being written by the 4 dequant groups + 2 queued for the tensor core),
+  // 4-6 packed stages (deeper packed rings did not help: the k-block time was the dequant warps' latency chain)
 #define B2Q_MM_NTOK(T, BITS, AS)                                                                  \
-  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, (BITS == 4 ? 8 : 6), 3>(a, x, ks)                 \
-   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, (BITS == 4 ? 7 : 5), 3>(a, x, ks)                 \
-   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, (BITS == 4 ? 9 : 7), 3>(a, x, ks)                 \
-               : launch_midm_t<T, BITS, AS, 128, (BITS == 4 ? 6 : 5), 3>(a, x, ks))
+  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, 6, 6>(a, x, ks)                                   \
+   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, 6, 6>(a, x, ks)                                   \
+   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, 6, 6>(a, x, ks)                                   \
+               : launch_midm_t<T, BITS, AS, 128, (BITS == 4 ? 5 : 4), 6>(a, x, ks))
 #define B2Q_MM_CASE(T)                                                          \
   (a.bits == 4 ? (asym ? B2Q_MM_NTOK(T, 4, true) : B2Q_MM_NTOK(T, 4, false))   \
                : (asym ? B2Q_MM_NTOK(T, 8, true) : B2Q_MM_NTOK(T, 8, false)))
   return a.dtype == 0 ? B2Q_MM_CASE(__half) : B2Q_MM_CASE(__nv_bfloat16);
 #undef B2Q_MM_CASE
 #undef B2Q_MM_NTOK
+}
+
+// ------------------------------------------------------------------------------------------------
+// grouped launches for a MoE block (b2q_moe.cu): a = {x = expert-sorted activations [rows, K], packed / scales / qzeros =
+// the STACKED tensors of all experts (expert stride = one expert's tensor), out = h [rows, N] (mode 1), M = token-box
+// width hint (largest row count one expert is expected to get), N / K of ONE expert}
+int midm_grouped_ranks(int K, int N, int active) {
+  const int tiles = (N + MM_BF - 1) / MM_BF, nkb = K / MM_BK;
+  int ks = 1;
+  while (ks < 8 && tiles * active * ks * 2 <= 148 && nkb / (ks * 2) >= 4) ks *= 2;
+  return ks;
+}
+
+int launch_midm_grouped(int mode, const MmArgs& a, const MoeGroupedArgs& g) {
+  if (a.bits != 4 || a.K % MM_BK != 0 || a.N % 32 != 0 || (mode != 1 && mode != 2) || g.E < 1 || g.rows < 1) {
+    set_error("b2q_moe: grouped launch needs bits=4, K %% 64 == 0, N %% 32 == 0 (bits=%d K=%d N=%d E=%d rows=%d)", a.bits,
+              a.K, a.N, g.E, g.rows);
+    return -1;
+  }
+  MoeArgs G = {};
+  G.counts = g.counts;
+  G.offsets = g.offsets;
+  G.sorted_pairs = g.sorted_pairs;
+  G.pair_weights = g.pair_weights;
+  G.packed3 = (const uint4*)g.packed3;
+  G.scales3 = g.scales3;
+  G.qzeros3 = (const uint32_t*)g.qzeros3;
+  G.ypair = g.ypair;
+  // token-box width: every expert may receive up to `rows` rows; boxes of 16 serve decode-sized batches with one block
+  // per expert, larger batches take 128-row blocks (CTAs of blocks beyond an expert's count exit immediately)
+  const int ntok = g.rows <= 16 ? 16 : g.rows <= 32 ? 32 : g.rows <= 64 ? 64 : 128;
+  G.tblocks = (g.rows + ntok - 1) / ntok;
+  const int grid_z = g.E * G.tblocks;
+  int ks = env().midm_ks > 0 ? env().midm_ks : midm_grouped_ranks(a.K, a.N, g.active > 0 ? g.active : 1);
+  if (ks > 8) ks = 8;
+  const int nkb = a.K / MM_BK;
+  while (ks > 1 && (ks - 1) * ((nkb + ks - 1) / ks) >= nkb) ks >>= 1;
+  const bool asym = a.qzeros != nullptr;
+#define B2Q_MG_NTOK(T, AS, MODE)                                                             \
+  (ntok == 16   ? launch_midm_t<T, 4, AS, 16, 6, 6, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+   : ntok == 32 ? launch_midm_t<T, 4, AS, 32, 6, 6, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+   : ntok == 64 ? launch_midm_t<T, 4, AS, 64, 6, 6, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+                : launch_midm_t<T, 4, AS, 128, 5, 6, MODE>(a, a.x, ks, G, g.rows, grid_z))
+#define B2Q_MG_CASE(T)                                                                       \
+  (mode == 1 ? (asym ? B2Q_MG_NTOK(T, true, 1) : B2Q_MG_NTOK(T, false, 1))                   \
+             : (asym ? B2Q_MG_NTOK(T, true, 2) : B2Q_MG_NTOK(T, false, 2)))
+  return a.dtype == 0 ? B2Q_MG_CASE(__half) : B2Q_MG_CASE(__nv_bfloat16);
+#undef B2Q_MG_CASE
+#undef B2Q_MG_NTOK
 }
 
 }  // namespace b2q

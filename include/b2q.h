@@ -93,6 +93,30 @@ int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const 
                      const int32_t* const* qzeros, const int32_t* perm, const void* const* bias, void* const* out,
                      const int* N, int M, int K, int bits, int group_size, int dtype, void* stream);
 
+/* ---- Grouped MoE expert path (BASELINE configs[4]; the reference's unused analogue: swordfish_moe.cu:9-17,38-48) --------
+ * y[t] = sum_j w[t, j] * W2_e( silu(W1_e x[t]) * W3_e x[t] ),  e = topk_ids[t, j], in FIVE launches without any host
+ * synchronisation (CUDA-graph capturable).  Expert weights are the b2q_prepack'ed tensors of the per-expert QuantLinears
+ * STACKED along a leading expert dimension (packed [E][K*N/2 bytes], scales [E][G][N], qzeros [E][G][N/8] or NULL when every
+ * expert is symmetric); 4-bit, any supported group size, no act-order.  rows = T * top_k (token, j) pairs; pair p = t*top_k+j.
+ *   b2q_moe_align   : topk_ids int32 [T, top_k] -> counts [E], offsets [E], sorted_pairs [rows] (stable by expert)
+ *   b2q_moe_gather  : xs [rows, K]  <- x[sorted_pairs[i] / top_k]
+ *   b2q_moe_gate_up : h [rows, N]   <- silu(xs W1_e) * (xs W3_e), both weight sets in one launch (rounded to the 16-bit
+ *                     dtype at every module boundary of the reference's per-expert loop); `active` = experts expected to
+ *                     receive rows (grid sizing only, e.g. min(E, rows))
+ *   b2q_moe_down    : ypair [rows, N] fp32, row = PAIR index <- pair_weights[p] * T(h W2_e)   (K = intermediate size)
+ *   b2q_moe_combine : y [T, N]      <- sum over the top_k slots of each token, one rounding */
+int b2q_moe_align(const int32_t* topk_ids, int T, int top_k, int E, int32_t* counts, int32_t* offsets,
+                  int32_t* sorted_pairs, void* stream);
+int b2q_moe_gather(const void* x, const int32_t* sorted_pairs, void* xs, int rows, int top_k, int K, void* stream);
+int b2q_moe_gate_up(const void* xs, const void* packed1, const void* scales1, const int32_t* qzeros1,
+                    const void* packed3, const void* scales3, const int32_t* qzeros3, void* h, const int32_t* counts,
+                    const int32_t* offsets, int E, int rows, int active, int K, int N, int bits, int group_size, int dtype,
+                    void* stream);
+int b2q_moe_down(const void* h, const void* packed2, const void* scales2, const int32_t* qzeros2, const int32_t* counts,
+                 const int32_t* offsets, const int32_t* sorted_pairs, const float* pair_weights, float* ypair, int E,
+                 int rows, int active, int K, int N, int bits, int group_size, int dtype, void* stream);
+int b2q_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int dtype, void* stream);
+
 /* In-place all-reduce(sum) of a small 16-bit vector (n % 8 == 0, n <= max_elems) across `world` <= 8 GPUs of one
  * NVLink domain: the single collective of a row-parallel QuantLinear at decode time (the reference has
  * none).  peer_bufs is a HOST array of `world` device pointers to every rank's symmetric buffer (this rank's included),

@@ -148,8 +148,10 @@ def test_decode2_index_model(K, N):
 
 def test_decode2_index_model_forced_groups(monkeypatch):
     # B2Q_DECODE2_GW forces the warps-per-group split: exercise 1, 2, 4, 8-warp groups explicitly
+    import gptqmodel_b200 as g
     for gw in (1, 2, 4, 8, 16):
         monkeypatch.setenv("B2Q_DECODE2_GW", str(gw))
+        g.lib.b2q_debug_reload_env()  # the switches are read once at load, never on the call path
         for (K, N) in ((4096, 4096), (4096, 7168), (1024, 2048)):
             for M in (1, 4):
                 for ks in (0, 2, 4):
@@ -158,3 +160,5 @@ def test_decode2_index_model_forced_groups(monkeypatch):
                         continue
                     assert p["gw"] == gw
                     simulate(M, K, N, p)
+    monkeypatch.delenv("B2Q_DECODE2_GW")
+    g.lib.b2q_debug_reload_env()

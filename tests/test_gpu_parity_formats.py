@@ -82,7 +82,7 @@ def test_dequantize_weight_bit_exact_on_gpu(bits, gs, sym, desc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("T", [3, 40])
+@pytest.mark.parametrize("T", [1, 3, 8, 40, 200])
 def test_moe_block_on_gpu(T):
     # BASELINE configs[4] in miniature: g64 asymmetric experts, top-2 routing, tokens grouped per expert (decode tier for
     # small blocks with w1/w3 in one launch, tensor-core tier for larger ones); single GPU -> no collective
@@ -106,9 +106,28 @@ def test_moe_block_on_gpu(T):
             xt = x[t:t + 1]
             h = (F.silu(oracle_forward(l1, xt).float()) * oracle_forward(l3, xt).float()).to(torch.float16)
             ref[t] += float(w[t, j]) * oracle_forward(l2, h)[0].float()
+    assert blk._stack is not None  # the grouped kernels serve this block (4-bit B200 experts of one shape)
     got = blk(x.cuda(), ids.cuda(), w.cuda())
     assert got.shape == (T, K) and got.dtype == torch.float16
     assert_close_rel(got, ref, 4e-3, f"moe T={T}")   # two chained fp16 layers + fp16 silu: a few ulp on top of 1e-3
+    # deterministic (no atomics), and the per-expert loop path (decode / small-batch / prefill tiers per expert block) agrees
+    assert torch.equal(got, blk(x.cuda(), ids.cuda(), w.cuda()))
+    loop = moe.MoEExperts(list(blk.w1), list(blk.w3), list(blk.w2), grouped=False)
+    assert loop._stack is None
+    assert_close_rel(loop(x.cuda(), ids.cuda(), w.cuda()), ref, 4e-3, f"moe loop path T={T}")
+    # the grouped block has no host synchronisation: it can be captured in a CUDA graph
+    xs, idc, wc = x.cuda(), ids.cuda(), w.cuda()
+    s_ = torch.cuda.Stream()
+    s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        blk(xs, idc, wc)
+    torch.cuda.current_stream().wait_stream(s_)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        yg = blk(xs, idc, wc)
+    gr.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(yg, got)
 
 
 @pytest.mark.gpu

@@ -118,8 +118,10 @@ def gemv2(MB=1):
 
         os.environ.pop("B2Q_DECODE2_GW", None)
         os.environ["B2Q_DECODE_V2"] = "0"
+        g.lib.b2q_debug_reload_env()
         v1 = run(0, 0)
         os.environ["B2Q_DECODE_V2"] = "1"
+        g.lib.b2q_debug_reload_env()
         v2 = run(0, 0)
         g.lib.b2q_debug_decode_plan(2, MB, K, N, 0, 0, plan)
         print(f"DECODE2 K={K} N={N} M={MB} alg={alg/1e6:.2f}MB  v1 {v1:.2f} us | v2 planner {v2:.2f} us "
@@ -132,6 +134,7 @@ def gemv2(MB=1):
                     if gw > warps or g.lib.b2q_debug_decode_plan(2, MB, K, N, ks, warps, plan) != 0:
                         continue
                     os.environ["B2Q_DECODE2_GW"] = str(gw)
+                    g.lib.b2q_debug_reload_env()
                     if g.lib.b2q_debug_decode_plan(2, MB, K, N, ks, warps, plan) != 0:
                         continue
                     try:
@@ -139,12 +142,14 @@ def gemv2(MB=1):
                     except Exception as e:  # noqa: BLE001
                         print("   fail", ks, warps, gw, e)
         os.environ.pop("B2Q_DECODE2_GW", None)
+        g.lib.b2q_debug_reload_env()
         res.sort()
         for us, ks, warps, gw, mt in res[:5]:
             print(f"   ks={ks} warps={warps:2d} gw={gw:2d} tiles/group={mt:2d}  {us:7.2f} us  frac={alg/us/1e3/PEAKS['hbm_gbs']:.3f}")
         del mods
         torch.cuda.empty_cache()
-    os.environ["B2Q_DECODE_V2"] = "0"
+    os.environ.pop("B2Q_DECODE_V2", None)
+    g.lib.b2q_debug_reload_env()
 
 
 def gemm(Ms=(2048,)):

@@ -1,6 +1,6 @@
 """Small-shape exercise of the experimental kernels (target for compute-sanitizer; also a quick parity check).
 
-    B2Q_DECODE_V2=1 B2Q_GEMM2_STREAMK=1 B2Q_GEMM_SPLITK=1 compute-sanitizer --tool memcheck python tools/san_one.py
+    B2Q_DECODE_V2=1 compute-sanitizer --tool memcheck python tools/san_one.py
     ... --tool racecheck / --tool synccheck
 
 Covers: decode v2 (sym / asym g64 / act-order, M = 1, 5, 8, single set and fused siblings, forced split-K and warp groups),
@@ -14,6 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gptqmodel_b200 as _g  # noqa: E402
 from gptqmodel_b200 import B200QuantLinear, fuse_siblings  # noqa: E402
 from helpers import assert_close_rel, make_layer, oracle_forward  # noqa: E402
 
@@ -43,8 +44,10 @@ for L in layers:
                 os.environ["B2Q_DECODE2_GW"] = gw
             else:
                 os.environ.pop("B2Q_DECODE2_GW", None)
+            _g.lib.b2q_debug_reload_env()
             check(m, L, M, f"decode K={L['K']} N={L['N']} g={L['group_size']} sym={L['sym']} act={L['desc_act']} M={M} gw={gw or 'auto'}")
     os.environ.pop("B2Q_DECODE2_GW", None)
+    _g.lib.b2q_debug_reload_env()
     for M in (40, 128, 300):
         check(m, L, M, f"gemm K={L['K']} N={L['N']} M={M}")
 # fused siblings through the multi-set path
@@ -56,8 +59,4 @@ for M in (1, 6):
     for m, L in zip(ms, Ls):
         assert_close_rel(m(x.cuda()), oracle_forward(L, x), 1e-3, f"fused M={M}")
     print("ok fused siblings M =", M, flush=True)
-# stream-K: 2 x 3 = 6 tiles, 5 x 2 = 10 tiles (all split), K large enough for several k-blocks per segment
-for (K, N, M) in ((512, 768, 300), (1024, 512, 1100)):
-    L = make_layer(K, N, group_size=128, sym=False, bias=True, seed=K + N)
-    check(mod(L), L, M, f"stream-K K={K} N={N} M={M}")
 print("all ok")
