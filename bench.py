@@ -108,8 +108,10 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------
-def synth_layer(K, N, seed, device, bits=4, gs=128):
-    """Random int4 codes + scales sized so activations stay O(1) through the 224-layer chain (sym, zero=8)."""
+def synth_layer(K, N, seed, device, bits=4, gs=128, perm=None, asym=False):
+    """Random int4 codes + scales sized so activations stay O(1) through the 224-layer chain (sym, zero=8).
+    perm: act-order (config 3): g_idx = (arange // gs)[perm].  asym (config 5): zero-points alternate 7 / 9 per column (a
+    real qzeros tensor the kernels must decode; the weights stay zero-mean so the chained activations stay finite)."""
     gen = torch.Generator(device=device).manual_seed(seed)
     # codes uniform in 1..15: zero-mean around the symmetric zero-point 8 (a non-zero weight mean would be amplified
     # ~sqrt(K) per layer and overflow fp16 after a few of the 224 chained layers)
@@ -117,26 +119,44 @@ def synth_layer(K, N, seed, device, bits=4, gs=128):
     for j in range(8):
         qw |= torch.randint(1, 16, (K // 8, N), dtype=torch.int32, device=device, generator=gen) << (4 * j)
     G = K // gs
-    qz = torch.full((G, N * bits // 32), 0x88888888 - (1 << 32), dtype=torch.int32, device=device)
+    zword = (0x97979797 - (1 << 32)) if asym else (0x88888888 - (1 << 32))
+    qz = torch.full((G, N * bits // 32), zword, dtype=torch.int32, device=device)
     base = 1.0 / (18.67 * K) ** 0.5  # var(q-8) = 18.67 for codes uniform in 1..15
     sc = ((0.8 + 0.4 * torch.rand(G, N, device=device, generator=gen)) * base).to(torch.float16)
     gi = torch.arange(K, dtype=torch.int32, device=device) // gs
+    if perm is not None:
+        gi = gi[perm.to(device).long()].contiguous()
     return dict(qweight=qw, qzeros=qz, scales=sc, g_idx=gi, bias=None, bits=bits, group_size=gs)
 
 
-def build_stack(device, rank, world, layers, fuse=True):
+def build_stack(device, rank, world, layers, fuse=True, cfg=None, desc_act=False, shard=None):
+    """cfg: model dims (default Llama-3-8B).  desc_act: act-order g_idx, one permutation per (layer, input) — q/k/v and
+    gate/up of a GPTQ checkpoint share theirs (same input Hessian).  shard=(r, w): build rank r's TP-w shards without a
+    process group (per-GPU work of a larger TP job, no collective)."""
     from gptqmodel_b200 import B200QuantLinear, fuse_siblings, tp
 
+    cfg = cfg or CFG
+    sr, sw = shard if shard is not None else (rank, world)
     stack = []
     for li in range(layers):
         mods = {}
+        perms = {}
         for j, (name, kk, nn_, style) in enumerate(LINEARS):
-            K, N = CFG[kk], CFG[nn_]
-            L = synth_layer(K, N, seed=li * 16 + j, device=device)
-            if world > 1:
-                L = tp.shard_columns(L, rank, world) if style == "col" else tp.shard_rows(L, rank, world)
-            m = B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], CFG["bits"],
-                                                        CFG["group_size"], device=device)
+            K, N = cfg[kk], cfg[nn_]
+            perm = None
+            if desc_act:
+                pk = {"q_proj": "h", "k_proj": "h", "v_proj": "h", "gate_proj": "h2", "up_proj": "h2"}.get(name, name)
+                if pk not in perms:
+                    perms[pk] = torch.randperm(K, generator=torch.Generator().manual_seed(li * 8 + len(perms)))
+                perm = perms[pk]
+            L = synth_layer(K, N, seed=li * 16 + j, device=device, gs=cfg["group_size"], perm=perm)
+            if sw > 1:
+                if style == "col" or desc_act:   # act-order row layers are served column-parallel (tp.GatheredColumnParallelLinear)
+                    L = tp.shard_columns(L, sr, sw)
+                else:
+                    L = tp.shard_rows(L, sr, sw)
+            m = B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], cfg["bits"],
+                                                        cfg["group_size"], desc_act=desc_act, device=device)
             mods[name] = m
             del L
         if fuse:
@@ -335,6 +355,153 @@ def reference_arm(args, rank):
     print(json.dumps(line))
 
 
+CFG70 = dict(name="Llama-3-70B", hidden=8192, inter=28672, kv=1024, layers=80, bits=4, group_size=128)
+MIXTRAL = dict(name="Mixtral-8x7B", hidden=4096, inter=14336, kv=1024, layers=32, experts=8, top_k=2, bits=4, group_size=64)
+
+
+def time_stack(stack, M, world, device, iters, hidden, runner=None):
+    """ms per pass of `stack` over M tokens (whole pass in one CUDA graph, CUDA events, max over ranks)."""
+    x = (torch.randn(M, hidden, device=device) * 0.5).to(torch.float16)
+    run = runner or run_stack
+    s_ = torch.cuda.Stream()
+    s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        for _ in range(2):
+            run(stack, x, world)
+    torch.cuda.current_stream().wait_stream(s_)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = run(stack, x, world)
+    for _ in range(3):
+        g.replay()
+    ms = timed_replays(g, iters, world, device) / iters
+    fin = bool(torch.isfinite(out).all())
+    del g
+    return ms, fin
+
+
+def stack_bytes_and_weights(cfg, layers, shard_world=1, M=1):
+    sizes = [(cfg[kk] // (shard_world if st == "row" else 1), cfg[nn_] // (shard_world if st == "col" else 1))
+             for _, kk, nn_, st in LINEARS]
+    alg = sum(algorithmic_bytes(K, N, cfg["group_size"], 4, M) for K, N in sizes) * layers
+    weights = sum(K * N for K, N in sizes) * layers
+    return alg, weights
+
+
+def build_mixtral(device, rank, world, layers, shard=None):
+    """Mixtral-8x7B int4 g64 ASYMMETRIC (BASELINE configs[4]): per layer q|k|v, o and the 8-expert MoE block (w1 / w3 column-,
+    w2 row-sharded, every rank holds a slice of every expert), experts through the GROUPED kernels (no host sync)."""
+    from gptqmodel_b200 import B200QuantLinear, fuse_siblings, moe, tp
+
+    c = MIXTRAL
+    sr, sw = shard if shard is not None else (rank, world)
+    mk = lambda L: B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], 4,  # noqa: E731
+                                                           c["group_size"], sym=False, device=device)
+    col = (lambda L: tp.shard_columns(L, sr, sw)) if sw > 1 else (lambda L: L)
+    row = (lambda L: tp.shard_rows(L, sr, sw)) if sw > 1 else (lambda L: L)
+    gen = torch.Generator().manual_seed(0)
+    stack = []
+    for li in range(layers):
+        sl = lambda K, N, j: synth_layer(K, N, seed=li * 64 + j, device=device, gs=c["group_size"], asym=True)  # noqa: E731
+        q, k, v = (mk(col(sl(c["hidden"], n, j))) for j, n in enumerate((c["hidden"], c["kv"], c["kv"])))
+        o = mk(row(sl(c["hidden"], c["hidden"], 3)))
+        fuse_siblings([q, k, v])
+        w1 = [mk(col(sl(c["hidden"], c["inter"], 4 + 3 * e))) for e in range(c["experts"])]
+        w3 = [mk(col(sl(c["hidden"], c["inter"], 5 + 3 * e))) for e in range(c["experts"])]
+        w2 = [mk(row(sl(c["inter"], c["hidden"], 6 + 3 * e))) for e in range(c["experts"])]
+        blk = moe.MoEExperts(w1, w3, w2, grouped=True)
+        logits = torch.randn(2048, c["experts"], generator=gen)
+        ids, w = moe.route_topk(logits, c["top_k"])
+        stack.append(dict(q=q, k=k, v=v, o=o, moe=blk, ids=ids.to(device), w=w.to(device)))
+    torch.cuda.empty_cache()
+    return stack
+
+
+def run_mixtral(stack, h, world):
+    M = h.shape[0]
+    for L in stack:
+        a = L["q"](h)
+        L["k"](h)
+        L["v"](h)
+        h2 = _row_parallel(L["o"], a, world)
+        h = L["moe"](h2, L["ids"][:M], L["w"][:M])   # ends in the block's single all-reduce when world > 1
+    return h
+
+
+def extra_workloads(args, device, rank, world, peaks):
+    """BASELINE configs 3-5 and the batched-decode regime, measured in the same run (VERDICT r01 missing #6)."""
+    extra = {}
+    hbm = peaks["hbm_gbs"]
+
+    def entry(name, fn):
+        try:
+            extra[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            extra[name] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.empty_cache()
+
+    if world == 1:
+        def act_order():
+            st = build_stack(device, 0, 1, CFG["layers"], fuse=True, desc_act=True)
+            alg, weights = stack_bytes_and_weights(CFG, CFG["layers"])
+            alg += 4 * sum(CFG[kk] for _, kk, _, _ in LINEARS) * CFG["layers"]   # + g_idx / perm reads
+            ms, fin = time_stack(st, 1, 1, device, 20, CFG["hidden"])
+            msp, _ = time_stack(st, args.prefill_tokens, 1, device, 3, CFG["hidden"])
+            return {"workload": "Llama-3-8B int4 g128 act-order (desc_act=True; q|k|v and gate|up share their g_idx), "
+                                "1xB200 (BASELINE configs[2])", "decode_tok_s": 1e3 / ms,
+                    "decode_frac_hbm": alg / (ms * 1e-3) / 1e9 / hbm,
+                    "prefill_tflops": 2.0 * args.prefill_tokens * weights / (msp * 1e-3) / 1e12, "finite": fin}
+        entry("act_order_8b", act_order)
+
+    def small_batch(stack):
+        out = {}
+        for M in (16, 64):
+            alg, _ = stack_bytes_and_weights(CFG, args.layers, world, M)
+            ms, fin = time_stack(stack, M, world, device, 10, CFG["hidden"])
+            out[f"M{M}"] = {"ms_per_step": ms, "tokens_per_s": M * 1e3 / ms, "frac_hbm": alg / (ms * 1e-3) / 1e9 / hbm,
+                            "finite": fin}
+        out["workload"] = "the same Llama-3-8B stack at 16 / 64 tokens per step (batched / speculative decode: small-batch tier)"
+        return out
+    extra["_small_batch_fn"] = small_batch
+
+    if world in (1, 8):
+        def l70():
+            shard = None if world == 8 else (0, 8)
+            st = build_stack(device, rank, world, CFG70["layers"], fuse=True, cfg=CFG70, shard=shard)
+            alg, weights = stack_bytes_and_weights(CFG70, CFG70["layers"], 8)
+            ms, fin = time_stack(st, 1, world, device, 10, CFG70["hidden"])
+            msp, _ = time_stack(st, args.prefill_tokens, world, device, 2, CFG70["hidden"])
+            return {"workload": "Llama-3-70B int4 g128, TP-8 (BASELINE configs[3])" + (
+                        "" if world == 8 else ": ONE rank's shard stack on one GPU, no all-reduce (per-GPU work only)"),
+                    "decode_tok_s": 1e3 / ms, "decode_frac_hbm_per_gpu": alg / (ms * 1e-3) / 1e9 / hbm,
+                    "prefill_tflops_per_gpu": 2.0 * args.prefill_tokens * weights / (msp * 1e-3) / 1e12,
+                    "prefill_ms": msp, "finite": fin}
+        entry("llama3_70b_tp8", l70)
+
+    if world in (1, 4):
+        def mixtral():
+            c = MIXTRAL
+            shard = None if world == 4 else (0, 4)
+            st = build_mixtral(device, rank, world, c["layers"], shard=shard)
+            # bytes per token per GPU: attention linears + the top-2 active experts (6.80 GB per token / 4)
+            att = sum(algorithmic_bytes(K, N, 64, 4, 1) for K, N in (
+                (c["hidden"], c["hidden"] // 4), (c["hidden"], c["kv"] // 4), (c["hidden"], c["kv"] // 4),
+                (c["hidden"] // 4, c["hidden"])))
+            exp = c["top_k"] * (2 * algorithmic_bytes(c["hidden"], c["inter"] // 4, 64, 4, 1) +
+                                algorithmic_bytes(c["inter"] // 4, c["hidden"], 64, 4, 1))
+            alg = (att + exp) * c["layers"]
+            ms, fin = time_stack(st, 1, world, device, 10, c["hidden"], runner=run_mixtral)
+            ms8, _ = time_stack(st, 8, world, device, 5, c["hidden"], runner=run_mixtral)
+            return {"workload": "Mixtral-8x7B int4 g64 asym, TP-4, experts through the grouped MoE kernels "
+                                "(BASELINE configs[4])" + ("" if world == 4 else
+                                                           ": ONE rank's shard stack on one GPU, no all-reduce"),
+                    "decode_tok_s": 1e3 / ms, "decode_frac_hbm_per_gpu": alg / (ms * 1e-3) / 1e9 / hbm,
+                    "decode_bytes_per_token_per_gpu": alg, "batch8_tokens_per_s": 8e3 / ms8, "finite": fin}
+        entry("mixtral_8x7b_tp4", mixtral)
+    return extra
+
+
 # ----------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -346,6 +513,9 @@ def main():
     ap.add_argument("--prefill-iters", type=int, default=0, help="0 = auto")
     ap.add_argument("--layers", type=int, default=CFG["layers"], help="debug: fewer layers (result marked invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads (BASELINE configs 3-5, batched decode)")
+    ap.add_argument("--no-competitors", action="store_true", help="skip the same-box Marlin comparison")
+    ap.add_argument("--with-vllm", action="store_true", help="competitors: also vLLM's Marlin build (import takes ~70 s)")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="keep NCCL for the small decode all-reduces (default: b2q_allreduce, our one-shot kernel over "
                          "NVLink peer memory; measured 715 vs 605 tok/s at TP-4)")
@@ -462,6 +632,29 @@ def main():
         torch.cuda.current_stream().synchronize()
     pre_e2e_ms = (time.perf_counter() - t0) / it_pre * 1e3
 
+    # ---------------- the other BASELINE configs + batched decode + competitor kernels ----------------
+    extra, competitors = {}, None
+    if not args.no_extra and args.layers == CFG["layers"]:
+        extra = extra_workloads(args, device, rank, world, peaks)
+        sb = extra.pop("_small_batch_fn")
+        try:
+            extra["small_batch"] = sb(stack)
+        except Exception as e:  # noqa: BLE001
+            extra["small_batch"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    if rank == 0 and world == 1 and not args.no_competitors and args.layers == CFG["layers"]:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import competitors as _comp
+
+            arms = ("b2q", "marlin_ref", "marlin_vllm") if args.with_vllm else ("b2q", "marlin_ref")
+            competitors = _comp.run(arms, Ms=(1, 16, 64, 2048), nlayers=CFG["layers"], stack=True, verbose=False)
+            competitors["note"] = ("same box, same packed checkpoint tensors; marlin_ref = the reference's own "
+                                   "gptqmodel_ext/marlin compiled for sm_100a by baseline/build_marlin.py; per-shape us = "
+                                   "mean over a CUDA graph walking >= 600 MB of distinct layers; stack = 224 separate "
+                                   "launches per step for every arm (this repo's headline additionally fuses q|k|v and gate|up)")
+        except Exception as e:  # noqa: BLE001
+            competitors = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -495,7 +688,8 @@ def main():
             "roofline": {
                 "kernel": ("decode2_kernel (EXPERIMENTAL b2q_decode2.cu: deferred tile epilogue, warp groups); "
                            if args.decode_v2 else
-                           "decode_kernel (fragment-major int4 -> mma.sync, bulk-copy ring, PDL); ")
+                           "decode tier (fragment-major int4 -> mma.sync, per-warp bulk-copy rings, PDL): decode2_kernel for "
+                           "the multi-tile q|k|v and gate|up launches, decode_kernel for o_proj / down_proj; ")
                           + ("one launch per QuantLinear" if args.no_fuse else
                              "q/k/v and gate/up siblings share a launch: 4 launches per decoder layer"),
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -524,6 +718,10 @@ def main():
             "clocks": clocks,
             "finite_outputs": finite,
         }
+        if extra:
+            line["extra"] = extra
+        if competitors is not None:
+            line["competitors"] = competitors
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if args.layers != CFG["layers"]:

@@ -31,7 +31,7 @@ static EnvCfg read_env() {
   c.decode_v2 = env_int("B2Q_DECODE_V2", -1);
   c.decode2_gw = env_int("B2Q_DECODE2_GW", 0);
   c.decode2_ks = env_int("B2Q_DECODE2_KS", 0);
-  c.decode2_xtma = env_int("B2Q_DECODE2_XTMA", 1);
+  c.decode2_xtma = env_int("B2Q_DECODE2_XTMA", 0);  // LDG staging measured faster (799.6 vs 789.1 tok/s, profiles/r02_decode_notes.md)
   c.decode2_fastsync = env_int("B2Q_DECODE2_FASTSYNC", 0);
   c.gemm2_persist = env_int("B2Q_GEMM2_PERSIST", 1);
   c.gemm2_dqw = env_int("B2Q_GEMM2_DQW", 8) == 4 ? 4 : 8;

@@ -85,7 +85,7 @@ struct EnvCfg {
   int decode_v2;        // B2Q_DECODE_V2=1 / 0  : force decode2_kernel / decode_kernel (default -1: per launch shape)
   int decode2_gw;       // B2Q_DECODE2_GW=n     : force warps per tile group of decode2_kernel
   int decode2_ks;       // B2Q_DECODE2_KS=n     : force its split-K cluster size
-  int decode2_xtma;     // B2Q_DECODE2_XTMA=0   : LDG staging instead of the bulk-copied activations
+  int decode2_xtma;     // B2Q_DECODE2_XTMA=1   : bulk-copied activations instead of the LDG staging loop (default 0)
   int decode2_fastsync; // B2Q_DECODE2_FASTSYNC=1: CTA-fenced cluster barriers
   int gemm2_persist;    // B2Q_GEMM2_PERSIST=0  : one tile per CTA pair
   int gemm2_dqw;        // B2Q_GEMM2_DQW=4

@@ -158,28 +158,28 @@ class Cublas:
 
 
 # ------------------------------------------------------------------------------------------------- driver
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--json", default=os.path.join(ROOT, "gpurun_out", "competitors.json"))
-    ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--arms", default="b2q,marlin_ref,marlin_vllm,cublas_fp16")
-    args = ap.parse_args()
-    torch.cuda.set_device(0)
-    res = {"gpu": torch.cuda.get_device_name(0), "arms": {}, "per_shape_us": {}, "stack": {}}
-    arms = []
+ARM_CLASSES = {}
+
+
+def run(arm_names=("b2q", "marlin_ref", "marlin_vllm", "cublas_fp16"), Ms=(1, 16, 64, 2048), nlayers=32, stack=True,
+        verbose=True):
+    """-> dict: per-shape microseconds at every M and whole-stack decode tok/s / prefill TFLOP/s per arm (same box, same
+    packed checkpoint tensors).  Used stand-alone and by bench.py's `competitors` block."""
     for cls in (B2Q, MarlinRef, MarlinVllm, Cublas):
-        if cls.name not in args.arms.split(","):
-            continue
+        ARM_CLASSES[cls.name] = cls
+    res = {"gpu": torch.cuda.get_device_name(torch.cuda.current_device()), "arms": {}, "per_shape_us": {}, "stack": {}}
+    arms = []
+    for name in arm_names:
         try:
-            a = cls()
+            a = ARM_CLASSES[name]()
             arms.append(a)
-            res["arms"][cls.name] = {"available": True, "info": a.info}
+            res["arms"][name] = {"available": True, "info": a.info}
         except Exception as e:  # noqa: BLE001
-            res["arms"][cls.name] = {"available": False, "why": f"{type(e).__name__}: {str(e)[:300]}"}
-    print(json.dumps(res["arms"], indent=1), flush=True)
+            res["arms"][name] = {"available": False, "why": f"{type(e).__name__}: {str(e)[:300]}"}
+    if verbose:
+        print(json.dumps(res["arms"], indent=1), flush=True)
 
     # ---- correctness of every arm against b2q on one layer, then per-shape timings
-    Ms = [1, 16, 64, 2048] if not args.quick else [1, 64]
     for K, N in SHAPES:
         copies = max(2, min(24, int(600e6 // (K * N // 2))))  # >= 600 MB of distinct weights per graph
         layers = [random_layer(K, N, 4, 128, True, seed=c, device="cuda") for c in range(copies)]
@@ -204,18 +204,18 @@ def main():
                             raise RuntimeError(f"output mismatch vs b2q: max abs diff "
                                                f"{(y.float() - yref.float()).abs().max().item():.3e}")
                     hs = handles[a.name]
-                    us = time_graph(lambda: [a.run(h, x) for h in hs]) / len(hs)
+                    us = time_graph(lambda: [a.run(h, x) for h in hs], iters=10) / len(hs)
                     res["per_shape_us"].setdefault(key, {}).setdefault(f"M{M}", {})[a.name] = round(us, 2)
                 except Exception as e:  # noqa: BLE001
                     res["per_shape_us"].setdefault(key, {}).setdefault(f"M{M}", {})[a.name] = f"ERR {str(e)[:160]}"
-            print(K, N, M, res["per_shape_us"][f"{K}x{N}"][f"M{M}"], flush=True)
+            if verbose:
+                print(K, N, M, res["per_shape_us"][f"{K}x{N}"][f"M{M}"], flush=True)
         del handles, layers
         torch.cuda.empty_cache()
 
     # ---- whole Llama-3-8B stack (32 x 7 QuantLinears, distinct weights): decode tok/s at M=1, prefill TFLOP/s at M=2048
-    nlayers = 8 if args.quick else 32
     flops = 2 * 2048 * sum(k * n for k, n in STACK) * nlayers
-    for a in arms:
+    for a in (arms if stack else []):
         if a.name == "cublas_fp16":
             continue
         try:
@@ -239,8 +239,20 @@ def main():
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             res["stack"][a.name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
-        print(a.name, res["stack"][a.name], flush=True)
+        if verbose:
+            print(a.name, res["stack"][a.name], flush=True)
+    return res
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--json", default=os.path.join(ROOT, "gpurun_out", "competitors.json"))
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--arms", default="b2q,marlin_ref,marlin_vllm,cublas_fp16")
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    res = run(tuple(args.arms.split(",")), Ms=(1, 64) if args.quick else (1, 16, 64, 2048),
+              nlayers=8 if args.quick else 32)
     os.makedirs(os.path.dirname(args.json), exist_ok=True)
     with open(args.json, "w") as f:
         json.dump(res, f, indent=1)
