@@ -36,6 +36,7 @@ static EnvCfg read_env() {
   c.gemm2_persist = env_int("B2Q_GEMM2_PERSIST", 1);
   c.gemm2_dqw = env_int("B2Q_GEMM2_DQW", 8) == 4 ? 4 : 8;
   c.midm_ks = env_int("B2Q_MIDM_KS", 0);
+  c.midm_dqg1 = env_int("B2Q_MIDM_DQG1", 0);
   return c;
 }
 

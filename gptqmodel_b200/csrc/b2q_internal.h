@@ -90,6 +90,7 @@ struct EnvCfg {
   int gemm2_persist;    // B2Q_GEMM2_PERSIST=0  : one tile per CTA pair
   int gemm2_dqw;        // B2Q_GEMM2_DQW=4
   int midm_ks;          // B2Q_MIDM_KS=n        : force the split-K cluster size of the small-batch tier
+  int midm_dqg1;        // B2Q_MIDM_DQG1=1      : all dequant warps of the small-batch tier on the same k-block (debugging)
 };
 const EnvCfg& env();
 void reload_env();

@@ -72,6 +72,7 @@ struct MidCfg {
   static_assert(PSTAGE_BYTES % 1024 == 0, "x tiles must stay 1024-byte aligned (SWIZZLE_128B atoms)");
   static_assert(PART_BYTES <= WST * W_BYTES + PST * PSTAGE_BYTES, "the fp32 partial tile reuses the idle stage buffers");
   static_assert((3 * PST + 2 * WST + 1) * 8 + 16 <= BAR_BYTES, "mbarrier area");
+  static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory of one CTA");
 };
 
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     // chains overlap and the tier becomes issue-bound instead.
     const int t = threadIdx.x - 64;  // 0..255
     constexpr int TG = MM_DQ_THREADS / DQG;
+    static_assert(PST % DQG == 0 && WST % DQG == 0, "every use of a ring stage must belong to the same dequant group");
     const int gq = t / TG, tl = t - gq * TG;
     constexpr int PF = 32 / BITS;
     constexpr int ZSYM = 1 << (BITS - 1);
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     } else {
       // 8-bit: a group covers the 128 feature rows x two 32-k halves of a block: thread -> rows tl + TG*r, both halves,
       // two uint4 (16 k each) per (row, half)
-      constexpr int R = 128 / TG;
+      constexpr int R = (128 / TG) > 0 ? 128 / TG : 1;  // (TG = 256 only exists for the 4-bit debug variant)
       for (int i = gq; i < NI; i += DQG) {
         const int kb = kb0 + i, s = i % PST, ws = i % WST;
         SZRaw sz[R][2];
@@ -476,13 +478,17 @@ int midm_ranks(int K, int N) {
 
 constexpr int MM_DQG = 4;  // dequant groups = k-blocks dequantised concurrently
 
-template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST, int MODE = 0>
+template <typename T, int BITS, bool ASYM, int NTOK, int PST, int WST, int MODE = 0, int DQG = MM_DQG>
 static int launch_midm_t(const MmArgs& a, const void* x, int ks, const MoeArgs& G = MoeArgs{}, int x_rows = 0,
                          int grid_z = 1) {
   using C = MidCfg<BITS, NTOK, PST, WST, MODE>;
+  if constexpr (BITS == 4 && MODE == 0 && DQG == MM_DQG) {
+    if (env().midm_dqg1)  // debugging: all dequant warps on the same k-block
+      return launch_midm_t<T, BITS, ASYM, NTOK, PST, WST, 0, 1>(a, x, ks, G, x_rows, grid_z);
+  }
   CUtensorMap tmap;
   if (make_x_tmap_box(&tmap, x, MODE == 0 ? a.M : x_rows, a.K, a.dtype, NTOK) != 0) return -1;
-  auto kern = midm_kernel<T, BITS, ASYM, NTOK, PST, WST, MODE, MM_DQG>;
+  auto kern = midm_kernel<T, BITS, ASYM, NTOK, PST, WST, MODE, DQG>;
   static uint32_t smem_ok = 0;  // per-device bit mask (a process may drive several GPUs)
   if (int e = ensure_dyn_smem(kern, C::SMEM_BYTES, smem_ok, "b2q_midm")) return e;
   const int nkb = a.K / MM_BK;
@@ -515,13 +521,17 @@ int launch_midm(const MmArgs& a, const void* x) {
   const int nkb = a.K / MM_BK;
   while (ks > 1 && (ks - 1) * ((nkb + ks - 1) / ks) >= nkb) ks >>= 1;  // every rank needs at least one k-block
   const bool asym = a.qzeros != nullptr;
-  // ring depths: WST = 6 dequantised stages (4 being written by the 4 dequant groups + 2 queued for the tensor core),
-  // 4-6 packed stages (deeper packed rings did not help: the k-block time was the dequant warps' latency chain)
+  // ring depths: BOTH must be multiples of the number of dequant groups, so that every use of a stage is served by the
+  // SAME group.  mbarrier waits only distinguish the parity of a phase: with 6-stage rings and 4 groups (first version)
+  // consecutive uses of a stage belonged to different groups, a group that ran two uses ahead saw the phase of use u - 2 as
+  // "its" completed phase, consumed a stage that had not been refilled and corrupted the arrival counts — every
+  // single-launch parity test and all three sanitizer tools passed, back-to-back launches at full size faulted
+  // (profiles/r02_midm_notes.md).  8 dequantised stages = two per group; 4-8 packed stages.
 #define B2Q_MM_NTOK(T, BITS, AS)                                                                  \
-  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, 6, 6>(a, x, ks)                                   \
-   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, 6, 6>(a, x, ks)                                   \
-   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, 6, 6>(a, x, ks)                                   \
-               : launch_midm_t<T, BITS, AS, 128, (BITS == 4 ? 5 : 4), 6>(a, x, ks))
+  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, 8, 8>(a, x, ks)                                   \
+   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, (BITS == 4 ? 8 : 4), 8>(a, x, ks)                 \
+   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, 4, 8>(a, x, ks)                                   \
+               : launch_midm_t<T, BITS, AS, 128, 4, 8>(a, x, ks))
 #define B2Q_MM_CASE(T)                                                          \
   (a.bits == 4 ? (asym ? B2Q_MM_NTOK(T, 4, true) : B2Q_MM_NTOK(T, 4, false))   \
                : (asym ? B2Q_MM_NTOK(T, 8, true) : B2Q_MM_NTOK(T, 8, false)))
@@ -567,10 +577,10 @@ int launch_midm_grouped(int mode, const MmArgs& a, const MoeGroupedArgs& g) {
   while (ks > 1 && (ks - 1) * ((nkb + ks - 1) / ks) >= nkb) ks >>= 1;
   const bool asym = a.qzeros != nullptr;
 #define B2Q_MG_NTOK(T, AS, MODE)                                                             \
-  (ntok == 16   ? launch_midm_t<T, 4, AS, 16, 6, 6, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
-   : ntok == 32 ? launch_midm_t<T, 4, AS, 32, 6, 6, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
-   : ntok == 64 ? launch_midm_t<T, 4, AS, 64, 6, 6, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
-                : launch_midm_t<T, 4, AS, 128, 5, 6, MODE>(a, a.x, ks, G, g.rows, grid_z))
+  (ntok == 16   ? launch_midm_t<T, 4, AS, 16, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+   : ntok == 32 ? launch_midm_t<T, 4, AS, 32, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+   : ntok == 64 ? launch_midm_t<T, 4, AS, 64, 4, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+                : launch_midm_t<T, 4, AS, 128, 4, 8, MODE>(a, a.x, ks, G, g.rows, grid_z))
 #define B2Q_MG_CASE(T)                                                                       \
   (mode == 1 ? (asym ? B2Q_MG_NTOK(T, true, 1) : B2Q_MG_NTOK(T, false, 1))                   \
              : (asym ? B2Q_MG_NTOK(T, true, 2) : B2Q_MG_NTOK(T, false, 2)))
