@@ -435,11 +435,14 @@ def extra_workloads(args, device, rank, world, peaks):
     hbm = peaks["hbm_gbs"]
 
     def entry(name, fn):
+        t0 = time.perf_counter()
         try:
             extra[name] = fn()
         except Exception as e:  # noqa: BLE001
             extra[name] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
         torch.cuda.empty_cache()
+        if rank == 0:
+            print(f"[bench] extra.{name}: {time.perf_counter() - t0:.1f} s", file=sys.stderr, flush=True)
 
     if world == 1:
         def act_order():
@@ -566,7 +569,14 @@ def main():
         global FUSED_AR
         FUSED_AR = _tp.FusedDecodeAllReduce(device, max_elems=8 * CFG["hidden"])
 
+    _t0 = time.perf_counter()
+
+    def phase(msg):
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - _t0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     stack = build_stack(device, rank, world, args.layers, fuse=not args.no_fuse)
+    phase("stack built")
     hidden = CFG["hidden"]
     sizes = [(CFG[kk] // (world if st == "row" else 1), CFG[nn_] // (world if st == "col" else 1))
              for _, kk, nn_, st in LINEARS]
@@ -607,6 +617,7 @@ def main():
         e2e_s = float(t.item())
     e2e_toks = args.steps / e2e_s
 
+    phase("decode timed")
     # ---------------- prefill: M tokens through the same 224 layers ----------------
     Mp = args.prefill_tokens
     xp = (torch.randn(Mp, hidden, device=device) * 0.5).to(torch.float16)
@@ -632,6 +643,7 @@ def main():
         torch.cuda.current_stream().synchronize()
     pre_e2e_ms = (time.perf_counter() - t0) / it_pre * 1e3
 
+    phase("prefill timed")
     # ---------------- the other BASELINE configs + batched decode + competitor kernels ----------------
     extra, competitors = {}, None
     if not args.no_extra and args.layers == CFG["layers"]:
@@ -641,6 +653,7 @@ def main():
             extra["small_batch"] = sb(stack)
         except Exception as e:  # noqa: BLE001
             extra["small_batch"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    phase("extra workloads done")
     if rank == 0 and world == 1 and not args.no_competitors and args.layers == CFG["layers"]:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -655,6 +668,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             competitors = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
+    phase("competitors done")
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -664,6 +678,7 @@ def main():
                     "sample": arm.describe(r)}
         del arm
 
+    phase("cpu baseline done")
     if rank == 0:
         achieved = alg_bytes_step / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU
         tr = load_traffic()

@@ -9,10 +9,12 @@
 //   4. sum  : the `world` rows are summed in rank order in fp32 (identical result on every rank) and rounded once
 // seq lives in device memory and only grows, so nothing is ever reset: CUDA-graph replay safe.  Slots alternate with
 // seq, so a fast rank's call n+1 never overwrites data a slow rank is still reading for call n.
+// The flag wait is bounded (2 s of %globaltimer): a dead peer leaves 1 + its rank in seq[1] instead of hanging the GPU.
 // One CTA, no NCCL, ~4 us instead of NCCL's LL all-reduce; the reference has no collective at all.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "b2q_common.cuh"
 #include "b2q_internal.h"
 
 namespace b2q {
@@ -52,8 +54,7 @@ __global__ void __launch_bounds__(256) allreduce_kernel(ARPeers peers, T* inout,
     st_release_sys_u32(peer_flags + slot * world + rank, seq + 1u);
     const uint32_t* my_flags =
         reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(peers.buf[rank]) + flag_offset);
-    while ((int32_t)(ld_acquire_sys_u32(my_flags + slot * world + r) - (seq + 1u)) < 0) {
-    }
+    if (!spin_until_geq_sys(my_flags + slot * world + r, seq + 1u)) seq_ptr[1] = 1u + (uint32_t)r;  // peer r is dead
   }
   __syncthreads();
   // 4. sum in rank order

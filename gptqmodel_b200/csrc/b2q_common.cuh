@@ -187,6 +187,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int fmt, int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- bounded spin on a flag another GPU writes (peer-memory all-reduce kernels) -------------------
+// A dead or wedged peer must not hang this GPU for ever: the wait gives up after
+// B2Q_PEER_TIMEOUT_NS of %globaltimer and the caller records 1 + peer rank in its status word.
+constexpr unsigned long long B2Q_PEER_TIMEOUT_NS = 2000000000ull;  // 2 s
+__device__ __forceinline__ bool spin_until_geq_sys(const uint32_t* p, uint32_t target) {
+  unsigned long long t0 = 0;
+  for (unsigned it = 0;; ++it) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if ((int32_t)(v - target) >= 0) return true;
+    if ((it & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > B2Q_PEER_TIMEOUT_NS) return false;
+    }
+  }
+}
+
 // ---- cluster helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -429,8 +429,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       dec_st_release_sys(peer_flags + ar.rank * DEC_AR_MAXCTA + cta, seq + 1u);
       const uint32_t* my_flags =
           reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ar.buf[ar.rank]) + ar.flag_offset);
-      while ((int32_t)(dec_ld_acquire_sys(my_flags + p * DEC_AR_MAXCTA + cta) - (seq + 1u)) < 0) {
-      }
+      if (!spin_until_geq_sys(my_flags + p * DEC_AR_MAXCTA + cta, seq + 1u)) ar.ctl[2] = 1u + (uint32_t)p;  // dead peer
     }
     __syncthreads();
     const float* mine = reinterpret_cast<const float*>(ar.buf[ar.rank]) + ar_slot * (size_t)ar.max_elems;

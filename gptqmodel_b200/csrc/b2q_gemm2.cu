@@ -231,8 +231,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + DQW * 32, 1)
 // dedicated group of 4 epilogue warps drains tile i while the mainloop already runs tile i+1; barrier init, TMEM
 // allocation, cluster syncs and the pipeline fill are paid once per CTA instead of once per tile (the per-tile fixed
 // cost of the non-persistent kernel was measured at ~7 us, profiles/r01_gemm_notes.md).
-//   warp 0 producer | warp 1 MMA (leader) | warps 2..5 dequant | warps 6..9 epilogue
-constexpr int G2P_THREADS = 320;
+//   warp 0 activation producer | warp 1 MMA (leader) | warps 2..5 dequant | warps 6..9 epilogue | warp 10 weight producer
+// (two producer threads: a single thread issuing the activation TMA AND the packed / scale / zero bulk copies of every
+//  k-block needs ~150 clk per asynchronous copy, 4-5 per block = the 770 clk per block this kernel was measured at against
+//  a 512 clk MMA floor — the same wall the small-batch tier hit, profiles/r02_midm_notes.md)
+constexpr int G2P_THREADS = 352;
 constexpr int G2P_TMEM_COLS = 512;
 
 template <typename T, bool ASYM>
@@ -288,12 +291,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
   const uint32_t tbase = *tmem_ptr;
 
   if (warp == 0) {
-    // ================================ producer ================================
+    // ================================ activation producer ================================
     if (lane == 0) {
       int kbc = 0;  // k-block counter across tiles (stage / phase bookkeeping)
       for (int tile = pair; tile < ntiles_total; tile += npairs) {
-        const int tm = tile % TM, tn = tile / TM;
-        const int n0 = tn * 256 + (int)rank * 128, m0 = tm * 256 + (int)rank * 128;
+        const int tm = tile % TM;
+        const int m0 = tm * 256 + (int)rank * 128;
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const int s = kbc % STAGES;
+          const uint32_t ph = (kbc / STAGES) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (rank == 0) mbar_expect_tx(bar_fullA + 8 * s, 2 * G2_A_BYTES);
+          tma_load_2d_cg2(sA + s * G2_A_BYTES, &tmap_x, mapa_u32(bar_fullA + 8 * s, 0), kb * G2_BK, m0);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ================================ weight producer ================================
+    if (lane == 0) {
+      int kbc = 0;
+      for (int tile = pair; tile < ntiles_total; tile += npairs) {
+        const int tn = tile / TM;
+        const int n0 = tn * 256 + (int)rank * 128;
         const int ft0 = n0 >> 4;
         const int nft = max(0, min(8, FT - ft0));
         const uint32_t pbytes = (uint32_t)nft * 512u;
@@ -301,8 +320,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
           const int s = kbc % STAGES;
           const uint32_t ph = (kbc / STAGES) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          if (rank == 0) mbar_expect_tx(bar_fullA + 8 * s, 2 * G2_A_BYTES);
-          tma_load_2d_cg2(sA + s * G2_A_BYTES, &tmap_x, mapa_u32(bar_fullA + 8 * s, 0), kb * G2_BK, m0);
           if (pbytes > 0) {
             const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
             const int nrows = (g1 != g0) ? 2 : 1;

@@ -14,8 +14,10 @@
 //     stores are 256 contiguous bytes per warp (features are the fast axis of `out`);
 //   * 8 dequant warps (one fragment-major uint4 = 2 features x 16 k per thread and k-block) produce the exact
 //     (q - z) * s operand (integer subtract first, ONE rounding: qlinear/__init__.py:1001-1003) as 16-byte swizzled
-//     K-major rows; separate mbarriers for the packed weights and for x let the weight stream + dequant of the first
-//     STAGES blocks run BEFORE griddepcontrol.wait (programmatic dependent launch), i.e. under the previous kernel's tail.
+//     K-major rows.  The dequant warps form 4 groups that take every 4th k-block; each group's leader issues the bulk copies of
+//     the group's own packed stages, warp 0 only the x tile TMA: no single thread issues every asynchronous copy of every
+//     k-block, and the weight stream + dequant of the first blocks run BEFORE griddepcontrol.wait (programmatic dependent
+//     launch), i.e. under the previous kernel's tail.
 // Reference counterparts: Swordfish's Stream-K / atomic split-K decode for 17 <= M < 128 (swordfish_mm.cu:113-154,
 // 229-276), its swapped-problem-shape tcgen05 trick (swordfish_prefill_impl.cuh:219-227), Marlin's small-M tiles
 // (marlin_template.h).
@@ -58,20 +60,21 @@ struct MoeArgs {
 template <int BITS, int NTOK, int PST, int WST, int MODE = 0>
 struct MidCfg {
   static constexpr int NSETS = MODE == 1 ? 2 : 1;
+  static constexpr int XST = NTOK >= 64 ? 4 : 8;         // activation-tile stages (own ring: one TMA per k-block)
   static constexpr int SUB = BITS / 4;
   static constexpr int W_BYTES = MM_BF * MM_BK * 2;      // dequantised weights, A operand: 16 KB
   static constexpr int X_BYTES = NTOK * MM_BK * 2;       // activations, B operand (first in its stage: 1024-B aligned)
   static constexpr int P_CHUNK_BYTES = 4 * SUB * 512;    // 8-bit: 4 feature tiles (of 32) x 32 k
   static constexpr int P_BYTES = 2 * P_CHUNK_BYTES + (BITS == 4 ? 1024 : 0);  // + scale / zero rows (4-bit)
-  static constexpr int PSTAGE_BYTES = X_BYTES + P_BYTES;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = WST * W_BYTES + PST * PSTAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int RING_BYTES = WST * W_BYTES + XST * X_BYTES + PST * P_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = NSETS * NTOK < 32 ? 32 : NSETS * NTOK;
   static constexpr int PART_BYTES = NSETS * NTOK * MM_BF * 4;  // fp32 partial tile(s) [set][token][feature]
   static_assert(MODE == 0 || BITS == 4, "the grouped (MoE) modes are built for 4-bit experts");
-  static_assert(PSTAGE_BYTES % 1024 == 0, "x tiles must stay 1024-byte aligned (SWIZZLE_128B atoms)");
-  static_assert(PART_BYTES <= WST * W_BYTES + PST * PSTAGE_BYTES, "the fp32 partial tile reuses the idle stage buffers");
-  static_assert((3 * PST + 2 * WST + 1) * 8 + 16 <= BAR_BYTES, "mbarrier area");
+  static_assert(X_BYTES % 1024 == 0, "x tiles must stay 1024-byte aligned (SWIZZLE_128B atoms)");
+  static_assert(PART_BYTES <= RING_BYTES, "the fp32 partial tile reuses the idle stage buffers");
+  static_assert((PST + 2 * XST + 2 * WST + 1) * 8 + 16 <= BAR_BYTES, "mbarrier area");
   static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory of one CTA");
 };
 
@@ -119,14 +122,16 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
+  constexpr int XST = C::XST;
   const uint32_t sW = smem_base;                      // [WST][128 features][64 k]      (also: fp32 partial tile)
-  const uint32_t sR = sW + WST * C::W_BYTES;          // [PST]{ x tile [NTOK][64 k] | packed codes | scale / zero rows }
-  const uint32_t sBar = sR + PST * C::PSTAGE_BYTES;
-  const uint32_t bar_pfull = sBar, bar_xfull = sBar + 8 * PST, bar_pempty = sBar + 16 * PST;
-  const uint32_t bar_wready = sBar + 24 * PST, bar_wempty = bar_wready + 8 * WST, bar_tfull = bar_wempty + 8 * WST;
+  const uint32_t sXr = sW + WST * C::W_BYTES;         // [XST] x tile [NTOK][64 k]
+  const uint32_t sPr = sXr + XST * C::X_BYTES;        // [PST]{ packed codes | scale / zero rows }
+  const uint32_t sBar = sPr + PST * C::P_BYTES;
+  const uint32_t bar_pfull = sBar, bar_xfull = bar_pfull + 8 * PST, bar_xempty = bar_xfull + 8 * XST;
+  const uint32_t bar_wready = bar_xempty + 8 * XST, bar_wempty = bar_wready + 8 * WST, bar_tfull = bar_wempty + 8 * WST;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + (bar_tfull - smem_base) + 8);
-  auto sXs = [&](int s) { return sR + (uint32_t)s * C::PSTAGE_BYTES; };
-  auto sPs = [&](int s) { return sR + (uint32_t)s * C::PSTAGE_BYTES + C::X_BYTES; };
+  auto sXs = [&](int s) { return sXr + (uint32_t)s * C::X_BYTES; };
+  auto sPs = [&](int s) { return sPr + (uint32_t)s * C::P_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = N >> 5;
@@ -144,10 +149,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
-    for (int s = 0; s < PST; ++s) {
-      mbar_init(bar_pfull + 8 * s, 1);
+    for (int s = 0; s < PST; ++s) mbar_init(bar_pfull + 8 * s, 1);
+    for (int s = 0; s < XST; ++s) {
       mbar_init(bar_xfull + 8 * s, 1);
-      mbar_init(bar_pempty + 8 * s, MM_DQ_THREADS / DQG + 1);  // the block's dequant group has read the codes + the MMA x
+      mbar_init(bar_xempty + 8 * s, 1);
     }
     for (int s = 0; s < WST; ++s) {
       mbar_init(bar_wready + 8 * s, MM_DQ_THREADS / DQG);
@@ -165,64 +170,59 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr;
 
-  if (warp == 0) {
-    // ================================ producer ================================
-    if (lane == 0) {
-      const int FT = N >> 4, ft0 = n0 >> 4;
-      const uint32_t pbytes4 = (uint32_t)min(8, FT - ft0) * 512u;
-      const uint32_t pbytes8 = (uint32_t)ntiles * C::SUB * 512u;
-      const uint32_t sbytes = (uint32_t)min(MM_BF, N - n0) * 2u, zbytes = ASYM ? sbytes / 4u : 0u;
-      auto load_weights = [&](int i, int s) {
-        const bool second = NSETS > 1 && i >= nkb;
-        const int kb = kb0 + (second ? i - nkb : i);
-        const uint4* pk = second ? packed_b : packed;
-        const T* sc = second ? scales_b : scales;
-        const uint32_t* zq = second ? qzeros_b : qzeros;
-        if (BITS == 4) {
-          // the scale / zero rows of the block's group(s) travel with the packed codes (no LDG in the dequant warps)
-          const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
-          const int nrows = (g1 != g0) ? 2 : 1;
-          mbar_expect_tx(bar_pfull + 8 * s, pbytes4 + nrows * (sbytes + zbytes));
-          bulk_load(sPs(s), pk + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_pfull + 8 * s);
-          for (int r = 0; r < nrows; ++r) {
-            const int gr = r ? g1 : g0;
-            bulk_load(sPs(s) + 4096 + r * 320, sc + (size_t)gr * N + n0, sbytes, bar_pfull + 8 * s);
-            if (ASYM)
-              bulk_load(sPs(s) + 4096 + r * 320 + 256, zq + (size_t)gr * (N >> 3) + (n0 >> 3), zbytes,
-                        bar_pfull + 8 * s);
-          }
-        } else {
-          mbar_expect_tx(bar_pfull + 8 * s, 2 * pbytes8);
+  // ---- weight loads of pipeline iteration i into packed stage s (issued by the LEADER of the dequant group that will
+  // consume the stage, see below: one thread per SM issuing every asynchronous copy of every k-block was the k-block time,
+  // ~150 clk per UBLKCP / UTMALDG from a single thread — profiles/r02_midm_notes.md)
+  const int FT = N >> 4, ft0 = n0 >> 4;
+  const uint32_t pbytes4 = (uint32_t)min(8, FT - ft0) * 512u;
+  const uint32_t pbytes8 = (uint32_t)ntiles * C::SUB * 512u;
+  const uint32_t sbytes = (uint32_t)min(MM_BF, N - n0) * 2u, zbytes = ASYM ? sbytes / 4u : 0u;
+  auto load_weights = [&](int i, int s) {
+    const bool second = NSETS > 1 && i >= nkb;
+    const int kb = kb0 + (second ? i - nkb : i);
+    const uint4* pk = second ? packed_b : packed;
+    const T* sc = second ? scales_b : scales;
+    const uint32_t* zq = second ? qzeros_b : qzeros;
+    if (BITS == 4) {
+      // the scale / zero rows of the block's group(s) travel with the packed codes (no LDG in the dequant warps)
+      const int g0 = (2 * kb) >> gshc, g1 = (2 * kb + 1) >> gshc;
+      const int nrows = (g1 != g0) ? 2 : 1;
+      mbar_expect_tx(bar_pfull + 8 * s, pbytes4 + nrows * (sbytes + zbytes));
+      bulk_load(sPs(s), pk + ((size_t)kb * FT + ft0) * 32, pbytes4, bar_pfull + 8 * s);
+      for (int r = 0; r < nrows; ++r) {
+        const int gr = r ? g1 : g0;
+        bulk_load(sPs(s) + 4096 + r * 320, sc + (size_t)gr * N + n0, sbytes, bar_pfull + 8 * s);
+        if (ASYM)
+          bulk_load(sPs(s) + 4096 + r * 320 + 256, zq + (size_t)gr * (N >> 3) + (n0 >> 3), zbytes, bar_pfull + 8 * s);
+      }
+    } else {
+      mbar_expect_tx(bar_pfull + 8 * s, 2 * pbytes8);
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            bulk_load(sPs(s) + j * C::P_CHUNK_BYTES, pk + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes8,
-                      bar_pfull + 8 * s);
-        }
-      };
-      auto load_x = [&](int i, int s) {
+      for (int j = 0; j < 2; ++j)
+        bulk_load(sPs(s) + j * C::P_CHUNK_BYTES, pk + ((size_t)(kb * 2 + j) * NT + nt0) * C::SUB * 32, pbytes8,
+                  bar_pfull + 8 * s);
+    }
+  };
+
+  if (warp == 0) {
+    // ================================ activation producer ================================
+    // one TMA per pipeline iteration: the x tile of the k-block (the weights are loaded by the dequant group leaders)
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // x is the previous kernel's output
+      for (int i = 0; i < NI; ++i) {
+        const int xs = i % XST;
+        if (i >= XST) mbar_wait(bar_xempty + 8 * xs, ((i / XST) & 1) ^ 1);
         const int kb = kb0 + ((NSETS > 1 && i >= nkb) ? i - nkb : i);
-        mbar_expect_tx(bar_xfull + 8 * s, C::X_BYTES);
-        tma_load_2d(sXs(s), &tmap_x, bar_xfull + 8 * s, kb * MM_BK, row0);
-      };
-      // weights never depend on the previous kernel: the first PST blocks stream (and are dequantised) before the
-      // producer of x has finished (MODE 0; the grouped modes had to wait for the routing tables at the very top)
-      const int pre = min(PST, NI);
-      for (int i = 0; i < pre; ++i) load_weights(i, i);
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (int i = 0; i < pre; ++i) load_x(i, i);
-      for (int i = pre; i < NI; ++i) {
-        const int s = i % PST;
-        mbar_wait(bar_pempty + 8 * s, ((i / PST) & 1) ^ 1);
-        load_weights(i, s);
-        load_x(i, s);
+        mbar_expect_tx(bar_xfull + 8 * xs, C::X_BYTES);
+        tma_load_2d(sXs(xs), &tmap_x, bar_xfull + 8 * xs, kb * MM_BK, row0);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = umma_idesc_f16(E::FMT, MM_BF, NTOK);
     for (int i = 0; i < NI; ++i) {
-      const int s = i % PST, ws = i % WST;
-      mbar_wait(bar_xfull + 8 * s, (i / PST) & 1);
+      const int xs = i % XST, ws = i % WST;
+      mbar_wait(bar_xfull + 8 * xs, (i / XST) & 1);
       mbar_wait(bar_wready + 8 * ws, (i / WST) & 1);
       tc_fence_after();
       if (lane == 0) {
@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
         const uint32_t dcol = tbase + (second ? NTOK : 0);          // set 1 accumulates in the next NTOK TMEM columns
         const int first = second ? nkb : 0;                         // first iteration of this set: overwrite
         const uint64_t wdesc = umma_desc_k_sw128(sW + ws * C::W_BYTES);
-        const uint64_t xdesc = umma_desc_k_sw128(sXs(s));
+        const uint64_t xdesc = umma_desc_k_sw128(sXs(xs));
 #pragma unroll
         for (int k = 0; k < MM_BK / 16; ++k)
           umma_f16(dcol, wdesc + 2 * k, xdesc + 2 * k, idesc, (i != first || k != 0) ? 1u : 0u);
         umma_commit(bar_wempty + 8 * ws);  // the dequantised stage may be overwritten
-        umma_commit(bar_pempty + 8 * s);   // the x tile of the packed stage has been read
+        umma_commit(bar_xempty + 8 * xs);  // the x tile has been read
         if (i == NI - 1) umma_commit(bar_tfull);
       }
       __syncwarp();
@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     const int gq = t / TG, tl = t - gq * TG;
     constexpr int PF = 32 / BITS;
     constexpr int ZSYM = 1 << (BITS - 1);
+    // the group's leader starts the weight stream of the group's first PST / DQG blocks (never depends on the previous
+    // kernel: under programmatic dependent launch this runs while the producer of x is still executing)
+    if (tl == 0)
+      for (int i = gq; i < NI && i < PST; i += DQG) load_weights(i, i);
     if (BITS == 4) {
       // DQG fragment-major uint4 per thread and iteration: q = tl + TG*u -> feature tile q>>5 (16 features), lane' = q&31
       constexpr int U = DQG;
@@ -282,7 +286,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
             zh[u] = (int)((zwh >> (4 * g)) & 15u);
           }
         }
-        mbar_arrive(bar_pempty + 8 * s);  // codes + scales are in registers: the producer may refill the packed stage
+        // codes + scales are in registers: once the whole group has read, its leader refills the stage for block i + PST
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + gq), "r"(TG) : "memory");
+        if (tl == 0 && i + PST < NI) load_weights(i + PST, s);
         if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);  // the MMA of block i - WST has read the stage
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -331,7 +337,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
             for (int h = 0; h < 2; ++h) pvs[r][j][h] = pj[((fr >> 5) * 2 + h) * 32 + (fr & 31)];
           }
         }
-        mbar_arrive(bar_pempty + 8 * s);  // codes are in registers: the producer may refill the packed stage
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + gq), "r"(TG) : "memory");  // codes are in registers: refill the stage
+        if (tl == 0 && i + PST < NI) load_weights(i + PST, s);
         if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -526,11 +533,12 @@ int launch_midm(const MmArgs& a, const void* x) {
   // consecutive uses of a stage belonged to different groups, a group that ran two uses ahead saw the phase of use u - 2 as
   // "its" completed phase, consumed a stage that had not been refilled and corrupted the arrival counts — every
   // single-launch parity test and all three sanitizer tools passed, back-to-back launches at full size faulted
-  // (profiles/r02_midm_notes.md).  8 dequantised stages = two per group; 4-8 packed stages.
+  // (profiles/r02_midm_notes.md).  8 dequantised stages = two per group; 4-8 packed stages (refilled by the group's own
+  // leader); 4-8 activation stages in their own ring.
 #define B2Q_MM_NTOK(T, BITS, AS)                                                                  \
   (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, 8, 8>(a, x, ks)                                   \
-   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, (BITS == 4 ? 8 : 4), 8>(a, x, ks)                 \
-   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, 4, 8>(a, x, ks)                                   \
+   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, 8, 8>(a, x, ks)                                   \
+   : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, (BITS == 4 ? 8 : 4), 8>(a, x, ks)                 \
                : launch_midm_t<T, BITS, AS, 128, 4, 8>(a, x, ks))
 #define B2Q_MM_CASE(T)                                                          \
   (a.bits == 4 ? (asym ? B2Q_MM_NTOK(T, 4, true) : B2Q_MM_NTOK(T, 4, false))   \
@@ -579,7 +587,7 @@ int launch_midm_grouped(int mode, const MmArgs& a, const MoeGroupedArgs& g) {
 #define B2Q_MG_NTOK(T, AS, MODE)                                                             \
   (ntok == 16   ? launch_midm_t<T, 4, AS, 16, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
    : ntok == 32 ? launch_midm_t<T, 4, AS, 32, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
-   : ntok == 64 ? launch_midm_t<T, 4, AS, 64, 4, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+   : ntok == 64 ? launch_midm_t<T, 4, AS, 64, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
                 : launch_midm_t<T, 4, AS, 128, 4, 8, MODE>(a, a.x, ks, G, g.rows, grid_z))
 #define B2Q_MG_CASE(T)                                                                       \
   (mode == 1 ? (asym ? B2Q_MG_NTOK(T, true, 1) : B2Q_MG_NTOK(T, false, 1))                   \

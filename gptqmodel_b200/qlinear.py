@@ -263,9 +263,10 @@ class B200KernelMixin:
             is_sym = bool((self.qzeros.data == zsym).all())
             packed = torch.empty(lib.b2q_packed_bytes(K, N, self.bits), dtype=torch.uint8, device=dev)
             qw = self.qweight.data.contiguous()
+            # (no stream synchronisation: the repack runs on the current stream and the caching allocator is stream-ordered,
+            #  so releasing the checkpoint-layout weights below is safe — 224 syncs per model load otherwise)
             check(lib.b2q_prepack(_ptr(qw), _ptr(perm), _ptr(packed), K, N, self.bits,
                                   torch.cuda.current_stream(dev).cuda_stream), "b2q_prepack")
-            torch.cuda.current_stream(dev).synchronize()
         self.packed = packed
         self.perm = perm
         self._zeros_dev = None if is_sym else self.qzeros.data.contiguous()

@@ -130,9 +130,13 @@ class P2PAllReduce:
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
         self._peers = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
-        self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        self.seq = torch.zeros(2, dtype=torch.int32, device=device)  # {call counter, status}
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's buffer is zeroed before anybody pushes into it
+
+    def status(self) -> int:
+        """0, or 1 + the rank of a peer whose flag never arrived within the kernel's 2 s bound (host sync; debugging)."""
+        return int(self.seq[1].item())
 
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
         from ._lib import check
@@ -205,7 +209,11 @@ class FusedDecodeAllReduce:
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
         self._peers = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
-        self.ctl = torch.zeros(2, dtype=torch.int32, device=device)
+        self.ctl = torch.zeros(4, dtype=torch.int32, device=device)  # {sequence, arrivals, status, -}
+
+    def status(self) -> int:
+        """0, or 1 + the rank of a peer whose flag never arrived within the kernel's 2 s bound (host sync; debugging)."""
+        return int(self.ctl[2].item())
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's buffer is zeroed before anybody pushes into it
 

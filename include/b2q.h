@@ -121,8 +121,9 @@ int b2q_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int dt
  * NVLink domain: the single collective of a row-parallel QuantLinear at decode time (the reference has
  * none).  peer_bufs is a HOST array of `world` device pointers to every rank's symmetric buffer (this rank's included),
  * each laid out as data[2][world][max_elems] (16-bit) followed at byte `flag_offset` by flags[2][world] (u32),
- * zero-initialised once; `seq` is a device u32 counter owned by this rank, zero-initialised once.  Every rank must
- * issue the same sequence of calls.  One CTA pushes, flags, waits and sums over peer memory; no NCCL. */
+ * zero-initialised once; `seq` is a device u32[2] owned by this rank, zero-initialised once: {call counter, status}.  Every
+ * rank must issue the same sequence of calls.  One CTA pushes, flags, waits and sums over peer memory; no NCCL.  The wait
+ * for a peer's flag is bounded (2 s): a dead peer leaves status = 1 + its rank instead of hanging the GPU. */
 int b2q_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs, size_t flag_offset,
                   int max_elems, void* seq, void* stream);
 
@@ -135,7 +136,7 @@ int b2q_allreduce(void* inout, int n, int dtype, int rank, int world, const void
  *   peer_bufs   : HOST array of `world` device pointers to every rank's symmetric buffer (this rank's included), laid
  *                 out as f32 data[2][world][max_elems], then at byte `flag_offset` (multiple of 16,
  *                 >= 2*world*max_elems*4) u32 flags of b2q_decode_allreduce_flag_bytes() bytes; zero-initialised once
- *   ctl         : this rank's device u32[2] {sequence, arrivals}, zero-initialised once
+ *   ctl         : this rank's device u32[4] {sequence, arrivals, status (1 + rank of a peer that timed out), -}, zeroed once
  * Every rank must issue the same sequence of calls with the same shapes.  CUDA-graph safe (nothing is reset).
  * EXPERIMENTAL in round 1: compiled, not yet validated on GPUs. */
 int b2q_decode_allreduce(const void* x, const void* packed, const void* scales, const int32_t* qzeros,
