@@ -370,18 +370,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
     }
   } else if (warp < 6) {
     // ================================ dequant warps ================================
-    // Each of the four dequant warps takes every 4th k-block (all 8 fragment-major uint4 rows of the block per lane)
-    // instead of all four warps sharing every block: one block is a serial chain of latencies for a warp (mbarrier wake-up,
-    // LDS, ALU, STS, fence.proxy.async, arrive: ~770 clk, which WAS the k-block time of this kernel against a 512 clk MMA
-    // floor — profiles/r01_gemm2_final.txt); with four blocks in flight the chains overlap and the tensor pipe is the limit.
-    const int dqw = warp - 2;  // 0..3
+    // (A variant in which each dequant warp took every 4th k-block passed the parity suite but could hang: with 5 stages and
+    //  4 warps consecutive uses of a stage belong to different warps, and an mbarrier parity wait cannot tell use u from
+    //  use u - 2 when the load of use u - 1 completes late — the same aliasing that faulted the small-batch tier; it also
+    //  bought nothing, the k-block time here is not the dequant chain.  profiles/r02_midm_notes.md)
+    const int t = threadIdx.x - 64;  // 0..127
     constexpr int ZSYM = 8;
-    const int g = lane >> 2, tt = lane & 3;
+    const int lp = t & 31, g = lp >> 2, tt = lp & 3;
+    int f[4];
+    f[0] = (t >> 5) * 16 + g;
+    f[1] = f[0] + 8;
+    f[2] = f[0] + 64;
+    f[3] = f[0] + 72;
     const uint32_t bready_leader = mapa_u32(bar_bready, 0);
     int kbc = 0;
     for (int tile = pair; tile < ntiles_total; tile += npairs) {
       for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-        if ((kbc & 3) != dqw) continue;
         const int s = kbc % STAGES;
         const uint32_t ph = (kbc / STAGES) & 1;
         mbar_wait(bar_fullP + 8 * s, ph);
@@ -389,39 +393,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
         const uint4* pj = reinterpret_cast<const uint4*>(pst);
         const int grow = ((2 * kb + (tt >> 1)) >> gshc) - ((2 * kb) >> gshc);  // 0 or 1
         const uint8_t* srow = pst + 4096 + grow * 320;
-        uint4 pv[8];
-        uint32_t s_lo[8], s_hi[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {  // feature tile u (16 features), this lane's rows u*16 + g and + 8
-          pv[u] = pj[lane + u * 32];
-          s_lo[u] = *reinterpret_cast<const uint16_t*>(srow + (u * 16 + g) * 2);
-          s_hi[u] = *reinterpret_cast<const uint16_t*>(srow + (u * 16 + g + 8) * 2);
-        }
-        uint32_t zw[4] = {0, 0, 0, 0};
-        if (ASYM) {
-          // packed zero words of the 128 features: word (u*16 + g) >> 3 = 2u (rows g) and 2u + 1 (rows g + 8)
-          const uint4 z0 = *reinterpret_cast<const uint4*>(srow + 256), z1 = *reinterpret_cast<const uint4*>(srow + 272);
-          const uint4 z2 = *reinterpret_cast<const uint4*>(srow + 288), z3 = *reinterpret_cast<const uint4*>(srow + 304);
-          (void)zw;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint4 zq = u < 2 ? z0 : (u < 4 ? z1 : (u < 6 ? z2 : z3));
-            const uint32_t wl = (u & 1) ? zq.z : zq.x, wh = (u & 1) ? zq.w : zq.y;
-            // stash the two nibbles in s_lo / s_hi's free upper halves
-            s_lo[u] |= ((wl >> (4 * g)) & 15u) << 16;
-            s_hi[u] |= ((wh >> (4 * g)) & 15u) << 16;
+        for (int u = 0; u < 2; ++u) {
+          const uint4 pv = pj[t + u * 128];
+          const uint32_t s_lo = *reinterpret_cast<const uint16_t*>(srow + f[2 * u] * 2);
+          const uint32_t s_hi = *reinterpret_cast<const uint16_t*>(srow + f[2 * u + 1] * 2);
+          int zl = ZSYM, zh = ZSYM;
+          if (ASYM) {
+            const uint32_t zwl = *reinterpret_cast<const uint32_t*>(srow + 256 + (f[2 * u] >> 3) * 4);
+            const uint32_t zwh = *reinterpret_cast<const uint32_t*>(srow + 256 + (f[2 * u + 1] >> 3) * 4);
+            zl = (int)((zwl >> (4 * g)) & 15u);
+            zh = (int)((zwh >> (4 * g)) & 15u);
           }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int zl = ASYM ? (int)(s_lo[u] >> 16) : ZSYM, zh = ASYM ? (int)(s_hi[u] >> 16) : ZSYM;
           uint4 lo[2], hi[2];
-          Dequant<T, 4>::run(pv[u], s_lo[u] & 0xffffu, zl, s_hi[u] & 0xffffu, zh, lo, hi);
-          const uint32_t rlo = sB + s * G2_B_BYTES + (u * 16 + g) * 128;
+          Dequant<T, 4>::run(pv, s_lo, zl, s_hi, zh, lo, hi);
+          const uint32_t sw = (uint32_t)g;
+          const uint32_t rlo = sB + s * G2_B_BYTES + f[2 * u] * 128;
           const uint32_t rhi = rlo + 8 * 128;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const uint32_t off = (((uint32_t)(2 * tt + c)) ^ (uint32_t)g) << 4;
+            const uint32_t off = (((uint32_t)(2 * tt + c)) ^ sw) << 4;
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rlo + off), "r"(lo[c].x), "r"(lo[c].y),
                          "r"(lo[c].z), "r"(lo[c].w)
                          : "memory");
@@ -431,8 +422,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
           }
         }
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(bready_leader + 8 * s);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t == 0) mbar_arrive_cluster(bready_leader + 8 * s);
       }
     }
   } else {

@@ -33,7 +33,7 @@ constexpr int MM_BF = 128;                  // features per tile (UMMA M)
 constexpr int MM_BK = 64;                   // k per block (one SWIZZLE_128B row of fp16)
 constexpr int MM_DQ_WARPS = 8;
 constexpr int MM_DQ_THREADS = MM_DQ_WARPS * 32;
-constexpr int MM_THREADS = 64 + MM_DQ_THREADS;
+constexpr int MM_THREADS = 64 + MM_DQ_THREADS + 32;  // producer, MMA issuer 0, 8 dequant warps, MMA issuer 1 (warp 10)
 
 // Two rings.  The PACKED ring (PST stages: x tile + packed codes + scale / zero rows, 7-21 KB each) is what hides the HBM
 // latency: with 4 stages (the first version of this kernel) only 16 KB of weights per SM were in flight and every k-block
@@ -69,7 +69,8 @@ struct MidCfg {
   static constexpr int BAR_BYTES = 512;
   static constexpr int RING_BYTES = WST * W_BYTES + XST * X_BYTES + PST * P_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = NSETS * NTOK < 32 ? 32 : NSETS * NTOK;
+  static constexpr int ACC_COLS = NSETS * NTOK;          // one accumulator set per MMA issuer (even / odd k-blocks)
+  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   static constexpr int PART_BYTES = NSETS * NTOK * MM_BF * 4;  // fp32 partial tile(s) [set][token][feature]
   static_assert(MODE == 0 || BITS == 4, "the grouped (MoE) modes are built for 4-bit experts");
   static_assert(X_BYTES % 1024 == 0, "x tiles must stay 1024-byte aligned (SWIZZLE_128B atoms)");
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
       mbar_init(bar_wready + 8 * s, MM_DQ_THREADS / DQG);
       mbar_init(bar_wempty + 8 * s, 1);
     }
-    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfull, nkb >= 2 ? 2 : 1);  // one arrival per active MMA issuer
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -217,18 +218,26 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
         tma_load_2d(sXs(xs), &tmap_x, bar_xfull + 8 * xs, kb * MM_BK, row0);
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 || warp == 10) {
+    // ================================ MMA issuers ================================
+    // TWO issuing warps take alternate pipeline iterations and accumulate into their OWN TMEM columns (summed in the
+    // epilogue: deterministic).  One thread issuing the two mbarrier waits, four tcgen05.mma and two or three
+    // tcgen05.commit of EVERY k-block was the k-block time of this tier (~770 clk at any token width, ring depth, dequant
+    // parallelism or copy-issue scheme: profiles/r02_midm_notes.md).
     constexpr uint32_t idesc = umma_idesc_f16(E::FMT, MM_BF, NTOK);
-    for (int i = 0; i < NI; ++i) {
+    const int nissue = nkb >= 2 ? 2 : 1;
+    const int mi = warp == 1 ? 0 : 1;
+    for (int i = mi; i < NI && mi < nissue; i += nissue) {
       const int xs = i % XST, ws = i % WST;
       mbar_wait(bar_xfull + 8 * xs, (i / XST) & 1);
       mbar_wait(bar_wready + 8 * ws, (i / WST) & 1);
       tc_fence_after();
       if (lane == 0) {
         const bool second = NSETS > 1 && i >= nkb;
-        const uint32_t dcol = tbase + (second ? NTOK : 0);          // set 1 accumulates in the next NTOK TMEM columns
-        const int first = second ? nkb : 0;                         // first iteration of this set: overwrite
+        // accumulator of (issuer mi, set): TMEM columns (mi * NSETS + set) * NTOK
+        const uint32_t dcol = tbase + (uint32_t)(mi * C::ACC_COLS + (second ? NTOK : 0));
+        const int start = second ? nkb : 0;
+        const int first = start + (((start & 1) != mi && nissue == 2) ? 1 : 0);  // this issuer's first block of the set
         const uint64_t wdesc = umma_desc_k_sw128(sW + ws * C::W_BYTES);
         const uint64_t xdesc = umma_desc_k_sw128(sXs(xs));
 #pragma unroll
@@ -236,11 +245,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
           umma_f16(dcol, wdesc + 2 * k, xdesc + 2 * k, idesc, (i != first || k != 0) ? 1u : 0u);
         umma_commit(bar_wempty + 8 * ws);  // the dequantised stage may be overwritten
         umma_commit(bar_xempty + 8 * xs);  // the x tile has been read
-        if (i == NI - 1) umma_commit(bar_tfull);
+        if (i + nissue >= NI) umma_commit(bar_tfull);  // this issuer's last block
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp < 10) {
     // ================================ dequant warps ================================
     // The dequant warps form DQG groups of TG threads; group gq takes the pipeline iterations i = gq, gq + DQG, ...  One
     // iteration is a serial chain of latencies for a warp (mbarrier wake-up, LDS, ~75 ALU instructions per uint4, STS,
@@ -379,9 +388,17 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     const int half = (warp - 2) >> 2;       // two warps share a quarter: they split the 16-token column chunks
     // column chunk c of 16 tokens; with two weight sets the chunks NTOK/16 .. 2*NTOK/16-1 are set 1 (TMEM columns and
     // partial-tile rows continue seamlessly: part[set * NTOK + token][feature])
+    const bool two = nkb >= 2;  // both MMA issuers own an accumulator
     for (int c = half; c < NSETS * NTOK / 16; c += 2) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
+      if (two) {
+        uint32_t r2[16];
+        tmem_ld_32x32b_x16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::ACC_COLS + c * 16), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 16; ++v) r[v] = __float_as_uint(__uint_as_float(r[v]) + __uint_as_float(r2[v]));
+      }
       tmem_ld_wait();
 #pragma unroll
       for (int v = 0; v < 16; ++v)
@@ -394,7 +411,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
   // all ranks' partials are in place (cluster barrier = CTA barrier + cross-CTA release / acquire)
   __syncwarp();
   cluster_sync_all();
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 10) {
     // rank z reduces token rows z, z + nrank, ... over all ranks through distributed shared memory; a warp owns one
     // token row at a time: 32 lanes x 4 features = the 128 features of the tile = 256 contiguous output bytes
     const int t = threadIdx.x - 64;

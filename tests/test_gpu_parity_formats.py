@@ -131,6 +131,28 @@ def test_moe_block_on_gpu(T):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sym,gs", [(True, 128), (False, 64)])
+def test_fused_gate_up_silu_epilogue_on_gpu(sym, gs):
+    # act_fn(gate_proj(x)) * up_proj(x) in one launch, SiLU-mul in the epilogue, rounding at the module
+    # boundaries of the reference's separate modules
+    import torch.nn.functional as F
+    from gptqmodel_b200 import B200QuantLinear
+    from gptqmodel_b200.mlp import FusedGateUpSilu
+    from helpers import oracle_forward
+    K, I = 512, 768
+    Lg, Lu = make_layer(K, I, group_size=gs, sym=sym, seed=91), make_layer(K, I, group_size=gs, sym=sym, seed=92)
+    mk = lambda L: B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], 4, gs,  # noqa: E731
+                                                           sym=sym)
+    fused = FusedGateUpSilu(mk(Lg), mk(Lu))
+    for M in (1, 7, 40, 128, 200):
+        x = (torch.randn(M, K, generator=torch.Generator().manual_seed(M)) * 0.5).to(torch.float16)
+        ref = (F.silu(oracle_forward(Lg, x).float()).to(torch.float16).float() * oracle_forward(Lu, x).float()).to(torch.float16)
+        got = fused(x.cuda())
+        assert got.shape == (M, I) and got.dtype == torch.float16
+        assert_close_rel(got, ref, 3e-3, f"gate/up silu M={M}")  # product of two 1e-3 factors + the fp16 silu rounding
+
+
+@pytest.mark.gpu
 def test_lora_adapter_epilogue_on_gpu():
     # forward() ends with adapter.apply(x=x, out=out) (reference contract, qlinear/marlin.py:333-335)
     from gptqmodel_b200 import B200QuantLinear, Lora
