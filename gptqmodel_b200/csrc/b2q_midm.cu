@@ -33,7 +33,7 @@ constexpr int MM_BF = 128;                  // features per tile (UMMA M)
 constexpr int MM_BK = 64;                   // k per block (one SWIZZLE_128B row of fp16)
 constexpr int MM_DQ_WARPS = 8;
 constexpr int MM_DQ_THREADS = MM_DQ_WARPS * 32;
-constexpr int MM_THREADS = 64 + MM_DQ_THREADS + 32;  // producer, MMA issuer 0, 8 dequant warps, MMA issuer 1 (warp 10)
+constexpr int MM_THREADS = 64 + MM_DQ_THREADS + 96;  // producer, MMA issuer 0, 8 dequant warps, MMA issuers 1..3 (warps 10..12)
 
 // Two rings.  The PACKED ring (PST stages: x tile + packed codes + scale / zero rows, 7-21 KB each) is what hides the HBM
 // latency: with 4 stages (the first version of this kernel) only 16 KB of weights per SM were in flight and every k-block
@@ -69,8 +69,10 @@ struct MidCfg {
   static constexpr int BAR_BYTES = 512;
   static constexpr int RING_BYTES = WST * W_BYTES + XST * X_BYTES + PST * P_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 1024;
-  static constexpr int ACC_COLS = NSETS * NTOK;          // one accumulator set per MMA issuer (even / odd k-blocks)
-  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  static constexpr int ACC_COLS = NSETS * NTOK;          // one accumulator set per MMA issuer
+  static constexpr int NISS = 4 * ACC_COLS <= 512 ? 4 : 2;  // MMA issuer warps (k-blocks i, i + NISS, ... each)
+  static constexpr int TMEM_COLS = NISS * ACC_COLS < 32 ? 32 : NISS * ACC_COLS;
+  static_assert(XST % NISS == 0 && WST % NISS == 0, "every use of a stage must belong to the same MMA issuer");
   static constexpr int PART_BYTES = NSETS * NTOK * MM_BF * 4;  // fp32 partial tile(s) [set][token][feature]
   static_assert(MODE == 0 || BITS == 4, "the grouped (MoE) modes are built for 4-bit experts");
   static_assert(X_BYTES % 1024 == 0, "x tiles must stay 1024-byte aligned (SWIZZLE_128B atoms)");
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
       mbar_init(bar_wready + 8 * s, MM_DQ_THREADS / DQG);
       mbar_init(bar_wempty + 8 * s, 1);
     }
-    mbar_init(bar_tfull, nkb >= 2 ? 2 : 1);  // one arrival per active MMA issuer
+    mbar_init(bar_tfull, nkb >= C::NISS ? C::NISS : (nkb >= 2 ? 2 : 1));  // one arrival per active MMA issuer
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -218,15 +220,15 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
         tma_load_2d(sXs(xs), &tmap_x, bar_xfull + 8 * xs, kb * MM_BK, row0);
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || warp >= 10) {
     // ================================ MMA issuers ================================
-    // TWO issuing warps take alternate pipeline iterations and accumulate into their OWN TMEM columns (summed in the
-    // epilogue: deterministic).  One thread issuing the two mbarrier waits, four tcgen05.mma and two or three
+    // Up to FOUR issuing warps take every NISS-th pipeline iteration and accumulate into their OWN TMEM columns (summed in
+    // the epilogue: deterministic).  One thread issuing the two mbarrier waits, four tcgen05.mma and two or three
     // tcgen05.commit of EVERY k-block was the k-block time of this tier (~770 clk at any token width, ring depth, dequant
     // parallelism or copy-issue scheme: profiles/r02_midm_notes.md).
     constexpr uint32_t idesc = umma_idesc_f16(E::FMT, MM_BF, NTOK);
-    const int nissue = nkb >= 2 ? 2 : 1;
-    const int mi = warp == 1 ? 0 : 1;
+    const int nissue = nkb >= C::NISS ? C::NISS : (nkb >= 2 ? 2 : 1);
+    const int mi = warp == 1 ? 0 : warp - 9;
     for (int i = mi; i < NI && mi < nissue; i += nissue) {
       const int xs = i % XST, ws = i % WST;
       mbar_wait(bar_xfull + 8 * xs, (i / XST) & 1);
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
         // accumulator of (issuer mi, set): TMEM columns (mi * NSETS + set) * NTOK
         const uint32_t dcol = tbase + (uint32_t)(mi * C::ACC_COLS + (second ? NTOK : 0));
         const int start = second ? nkb : 0;
-        const int first = start + (((start & 1) != mi && nissue == 2) ? 1 : 0);  // this issuer's first block of the set
+        const int first = start + ((mi - start % nissue + nissue) % nissue);  // this issuer's first block of the set
         const uint64_t wdesc = umma_desc_k_sw128(sW + ws * C::W_BYTES);
         const uint64_t xdesc = umma_desc_k_sw128(sXs(xs));
 #pragma unroll
@@ -388,18 +390,18 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
     const int half = (warp - 2) >> 2;       // two warps share a quarter: they split the 16-token column chunks
     // column chunk c of 16 tokens; with two weight sets the chunks NTOK/16 .. 2*NTOK/16-1 are set 1 (TMEM columns and
     // partial-tile rows continue seamlessly: part[set * NTOK + token][feature])
-    const bool two = nkb >= 2;  // both MMA issuers own an accumulator
+    const int nacc = nkb >= C::NISS ? C::NISS : (nkb >= 2 ? 2 : 1);  // accumulators in use (one per active MMA issuer)
     for (int c = half; c < NSETS * NTOK / 16; c += 2) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
-      if (two) {
+      tmem_ld_wait();
+      for (int ai = 1; ai < nacc; ++ai) {  // fixed order: deterministic
         uint32_t r2[16];
-        tmem_ld_32x32b_x16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::ACC_COLS + c * 16), r2);
+        tmem_ld_32x32b_x16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * C::ACC_COLS + c * 16), r2);
         tmem_ld_wait();
 #pragma unroll
         for (int v = 0; v < 16; ++v) r[v] = __float_as_uint(__uint_as_float(r[v]) + __uint_as_float(r2[v]));
       }
-      tmem_ld_wait();
 #pragma unroll
       for (int v = 0; v < 16; ++v)
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW + (uint32_t)(c * 16 + v) * (MM_BF * 4) + (uint32_t)(q * 32 + lane) * 4),
