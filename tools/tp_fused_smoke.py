@@ -29,6 +29,7 @@ for (K, N, sym, gs) in ((2048, 1024, True, 128), (4096, 4096, True, 128), (14336
     if (K // world) % gs or (K // world) % 128:
         continue
     full = random_layer(K, N, seed=K + N, sym=sym, group_size=gs, device="cuda")
+    torch.manual_seed(K + N)  # every rank must draw the SAME bias (rank 1's oracle was off by its own bias in the first run)
     full["bias"] = (torch.randn(N, device="cuda") * 0.1).to(torch.float16)
     sh = tp.shard_rows(full, rank, world)
     mod = B200QuantLinear.from_checkpoint_tensors(sh["qweight"], sh["qzeros"], sh["scales"], sh["g_idx"], 4, gs,
