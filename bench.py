@@ -174,14 +174,25 @@ P2P_AR = None  # optional gptqmodel_b200.tp.P2PAllReduce (--p2p-allreduce): our 
 FUSED_AR = None  # optional gptqmodel_b200.tp.FusedDecodeAllReduce (--fused-allreduce, experimental): matmul + all-reduce in one launch
 
 
+_RP_CACHE = {}
+
+
 def _row_parallel(mod, x, world):
-    """o_proj / down_proj: the shard's matmul followed by the all-reduce of the partial sums (world > 1)."""
-    if world > 1 and FUSED_AR is not None and x.shape[0] <= 8:
-        return mod.forward_allreduce(x, FUSED_AR)
-    y = mod(x)
-    if world > 1:
-        _all_reduce(y)
-    return y
+    """o_proj / down_proj: the library's row-parallel wrapper (gptqmodel_b200.tp.RowParallelLinear): shard matmul + ONE
+    all-reduce — the fused launch / our peer-memory kernel for decode-sized outputs, NCCL overlapped with the next token
+    block's GEMM for prefill-sized ones."""
+    if world == 1:
+        return mod(x)
+    rp = _RP_CACHE.get(id(mod))
+    if rp is None:
+        from gptqmodel_b200 import tp as _tp
+        rp = _tp.RowParallelLinear(mod, reduce=FUSED_AR if FUSED_AR is not None else P2P_AR,
+                                   overlap_chunks=OVERLAP_CHUNKS)
+        _RP_CACHE[id(mod)] = rp
+    return rp(x)
+
+
+OVERLAP_CHUNKS = 4
 
 
 def _all_reduce(t):
@@ -522,12 +533,16 @@ def main():
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="keep NCCL for the small decode all-reduces (default: b2q_allreduce, our one-shot kernel over "
                          "NVLink peer memory; measured 715 vs 605 tok/s at TP-4)")
+    ap.add_argument("--overlap-chunks", type=int, default=4,
+                    help="N > 1 prefill: token blocks whose all-reduce overlaps the next block's GEMM (1 = off)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinear (224/step) instead of fusing q/k/v and gate/up")
     ap.add_argument("--decode-v2", action="store_true",
                     help="EXPERIMENTAL: decode tier v2 (b2q_decode2.cu; sets B2Q_DECODE_V2=1), result marked experimental")
     ap.add_argument("--fused-allreduce", action="store_true",
                     help="EXPERIMENTAL (N > 1): row-parallel matmul + all-reduce in one launch (b2q_decode_allreduce)")
     args = ap.parse_args()
+    global OVERLAP_CHUNKS
+    OVERLAP_CHUNKS = args.overlap_chunks
     if args.decode_v2:
         os.environ["B2Q_DECODE_V2"] = "1"
 

@@ -320,6 +320,38 @@ int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const 
   return check_cuda(launch_decode_multi(a, nsets, packed, scales, qzeros, bias, out, N), "b2q_decode_multi");
 }
 
+int b2q_gemm_multi(const void* x, int nsets, const void* const* packed, const void* const* scales,
+                   const int32_t* const* qzeros, const int32_t* perm, const void* const* bias, void* const* out,
+                   const int* N, int M, int K, int bits, int group_size, int dtype, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (x == nullptr || packed == nullptr || scales == nullptr || qzeros == nullptr || bias == nullptr ||
+      out == nullptr || N == nullptr || nsets < 1) {
+    set_error("b2q_gemm_multi: null pointer argument");
+    return -2;
+  }
+  int v = validate("b2q_gemm_multi", x, packed[0], scales[0], out[0], M, K, N[0], bits, group_size, dtype);
+  if (v != 0) return v;
+  if (bits != 4 || M <= 128) {
+    set_error("b2q_gemm_multi: the fused prefill launch serves bits=4, M > 128 (got bits=%d M=%d)", bits, M);
+    return -2;
+  }
+  DeviceGuard dg(packed[0]);
+  MmArgs a = make_args(x, packed[0], scales[0], qzeros[0], perm, bias[0], out[0], M, K, N[0], bits, group_size, dtype,
+                       workspace, workspace_bytes, stream);
+  const void* xa = x;
+  if (perm != nullptr) {  // act-order siblings share g_idx: ONE gather of x serves all sets
+    const size_t need = (size_t)M * K * 2;
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("b2q_gemm_multi: act-order needs a %zu-byte workspace (got %zu)", need, workspace_bytes);
+      return -2;
+    }
+    int e = check_cuda(launch_permute_cols(x, perm, workspace, M, K, (cudaStream_t)stream), "b2q_gemm_multi(permute)");
+    if (e != 0) return e;
+    xa = workspace;
+  }
+  return check_cuda(launch_gemm2_multi(a, xa, nsets, packed, scales, qzeros, bias, out, N), "b2q_gemm_multi");
+}
+
 int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
              const void* bias, void* out, int M, int K, int N, int bits, int group_size, int dtype, void* workspace,
              size_t workspace_bytes, void* stream) {

@@ -236,13 +236,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + DQW * 32, 1)
 //  k-block needs ~150 clk per asynchronous copy, 4-5 per block = the 770 clk per block this kernel was measured at against
 //  a 512 clk MMA floor — the same wall the small-batch tier hit, profiles/r02_midm_notes.md)
 constexpr int G2P_THREADS = 352;
+
+// Sibling QuantLinears that consume the SAME activations (q|k|v, gate|up) share ONE persistent launch: the 256-feature tile
+// COLUMNS of all sets form one index space (tn_end = running totals), so the 74 CTA pairs see 192 / 896 tiles instead of
+// 128 + 32 + 32 / 448 + 448 — fewer partially filled waves and two launches less per layer.
+constexpr int G2_MAX_SETS = 3;
+struct G2Sets {
+  int nsets;
+  int tn_end[G2_MAX_SETS];
+  int N[G2_MAX_SETS];
+  const uint4* packed[G2_MAX_SETS];
+  const void* scales[G2_MAX_SETS];
+  const uint32_t* qzeros[G2_MAX_SETS];
+  const void* bias[G2_MAX_SETS];
+  void* out[G2_MAX_SETS];
+};
+struct G2Tile {
+  int set, tn;  // weight set and tile column inside it
+};
+__device__ __forceinline__ G2Tile g2_resolve(const G2Sets& S, int tn) {
+  G2Tile t;
+  t.set = 0;
+  t.tn = tn;
+  if (S.nsets > 1 && tn >= S.tn_end[0]) {
+    t.set = 1;
+    t.tn = tn - S.tn_end[0];
+    if (S.nsets > 2 && tn >= S.tn_end[1]) {
+      t.set = 2;
+      t.tn = tn - S.tn_end[1];
+    }
+  }
+  return t;
+}
 constexpr int G2P_TMEM_COLS = 512;
 
 template <typename T, bool ASYM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
-    gemm2p_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ packed,
-                  const T* __restrict__ scales, const uint32_t* __restrict__ qzeros, const T* __restrict__ bias,
-                  T* __restrict__ out, int M, int K, int N, int group_size, int gshc, int TM, int ntiles_total) {
+    gemm2p_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ G2Sets S, int M, int K,
+                  int group_size, int gshc, int TM, int ntiles_total) {
   using E = ET<T>;
   constexpr int STAGES = G2_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -261,7 +292,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int FT = N >> 4;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nkb = K / G2_BK;
 
@@ -311,8 +341,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
     if (lane == 0) {
       int kbc = 0;
       for (int tile = pair; tile < ntiles_total; tile += npairs) {
-        const int tn = tile / TM;
-        const int n0 = tn * 256 + (int)rank * 128;
+        const G2Tile gt = g2_resolve(S, tile / TM);
+        const int N = S.N[gt.set], FT = N >> 4;
+        const uint4* packed = S.packed[gt.set];
+        const T* scales = reinterpret_cast<const T*>(S.scales[gt.set]);
+        const uint32_t* qzeros = S.qzeros[gt.set];
+        const int n0 = gt.tn * 256 + (int)rank * 128;
         const int ft0 = n0 >> 4;
         const int nft = max(0, min(8, FT - ft0));
         const uint32_t pbytes = (uint32_t)nft * 512u;
@@ -433,8 +467,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
     int it = 0;
     for (int tile = pair; tile < ntiles_total; tile += npairs, ++it) {
       const int a = it & 1;
-      const int tm = tile % TM, tn = tile / TM;
-      const int npair0 = tn * 256, m0 = tm * 256 + (int)rank * 128;
+      const int tm = tile % TM;
+      const G2Tile gt = g2_resolve(S, tile / TM);
+      const int N = S.N[gt.set];
+      const T* bias = reinterpret_cast<const T*>(S.bias[gt.set]);
+      T* out = reinterpret_cast<T*>(S.out[gt.set]);
+      const int npair0 = gt.tn * 256, m0 = tm * 256 + (int)rank * 128;
       mbar_wait(bar_tfull + 8 * a, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -499,27 +537,69 @@ static int launch_gemm2_t(const MmArgs& a, const void* x) {
 }
 
 template <typename T, bool ASYM>
-static int launch_gemm2p_t(const MmArgs& a, const void* x) {
+static int launch_gemm2p_t(const MmArgs& a, const void* x, const G2Sets& S) {
   CUtensorMap tmap;
   if (make_x_tmap2(&tmap, x, a.M, a.K, a.dtype) != 0) return -1;
   auto kern = gemm2p_kernel<T, ASYM>;
   static uint32_t smem_ok = 0;
   if (int e = ensure_dyn_smem(kern, G2_SMEM_BYTES, smem_ok, "b2q_gemm2p")) return e;
-  const int TM = (a.M + 255) / 256, TN = (a.N + 255) / 256;
+  const int TM = (a.M + 255) / 256, TN = S.tn_end[S.nsets - 1];
   const int tiles = TM * TN;
   const int npairs = tiles < 74 ? tiles : 74;
-  kern<<<dim3(2 * npairs, 1, 1), G2P_THREADS, G2_SMEM_BYTES, a.stream>>>(
-      tmap, (const uint4*)a.packed, (const T*)a.scales, (const uint32_t*)a.qzeros, (const T*)a.bias, (T*)a.out, a.M,
-      a.K, a.N, a.group_size, gemm_gshc(a), TM, tiles);
+  kern<<<dim3(2 * npairs, 1, 1), G2P_THREADS, G2_SMEM_BYTES, a.stream>>>(tmap, S, a.M, a.K, a.group_size, gemm_gshc(a),
+                                                                         TM, tiles);
   return (int)cudaGetLastError();
+}
+
+static int launch_gemm2p_sets(const MmArgs& a, const void* x, const G2Sets& S) {
+  const bool asym = S.qzeros[0] != nullptr;
+  if (a.dtype == 0) return asym ? launch_gemm2p_t<__half, true>(a, x, S) : launch_gemm2p_t<__half, false>(a, x, S);
+  return asym ? launch_gemm2p_t<__nv_bfloat16, true>(a, x, S) : launch_gemm2p_t<__nv_bfloat16, false>(a, x, S);
+}
+
+// Sibling QuantLinears in one persistent launch (b2q_gemm_multi); x = activations with act-order already applied
+int launch_gemm2_multi(const MmArgs& a, const void* x, int nsets, const void* const* packed, const void* const* scales,
+                       const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* Ns) {
+  if (nsets < 1 || nsets > G2_MAX_SETS) {
+    set_error("b2q_gemm_multi: nsets=%d out of range (1..%d)", nsets, G2_MAX_SETS);
+    return -1;
+  }
+  G2Sets S = {};
+  S.nsets = nsets;
+  int tn = 0;
+  for (int i = 0; i < nsets; ++i) {
+    if (Ns[i] <= 0 || Ns[i] % 32 != 0 || packed[i] == nullptr || scales[i] == nullptr || out[i] == nullptr ||
+        ((qzeros[i] != nullptr) != (qzeros[0] != nullptr))) {
+      set_error("b2q_gemm_multi: set %d unsupported (N=%d; all sets share K, group size and symmetry)", i, Ns[i]);
+      return -1;
+    }
+    tn += (Ns[i] + 255) / 256;
+    S.tn_end[i] = tn;
+    S.N[i] = Ns[i];
+    S.packed[i] = (const uint4*)packed[i];
+    S.scales[i] = scales[i];
+    S.qzeros[i] = (const uint32_t*)qzeros[i];
+    S.bias[i] = bias[i];
+    S.out[i] = out[i];
+  }
+  for (int i = nsets; i < G2_MAX_SETS; ++i) S.tn_end[i] = tn;
+  return launch_gemm2p_sets(a, x, S);
 }
 
 // x must already be the (act-order permuted, if any) activation matrix
 int launch_gemm2(const MmArgs& a, const void* x) {
   const bool asym = a.qzeros != nullptr;
   if (env().gemm2_persist) {
-    if (a.dtype == 0) return asym ? launch_gemm2p_t<__half, true>(a, x) : launch_gemm2p_t<__half, false>(a, x);
-    return asym ? launch_gemm2p_t<__nv_bfloat16, true>(a, x) : launch_gemm2p_t<__nv_bfloat16, false>(a, x);
+    G2Sets S = {};
+    S.nsets = 1;
+    for (int i = 0; i < G2_MAX_SETS; ++i) S.tn_end[i] = (a.N + 255) / 256;
+    S.N[0] = a.N;
+    S.packed[0] = (const uint4*)a.packed;
+    S.scales[0] = a.scales;
+    S.qzeros[0] = (const uint32_t*)a.qzeros;
+    S.bias[0] = a.bias;
+    S.out[0] = a.out;
+    return launch_gemm2p_sets(a, x, S);
   }
   const int dqw = env().gemm2_dqw;
 #define B2Q_G2(T, AS) (dqw == 8 ? launch_gemm2_t<T, AS, 8>(a, x) : launch_gemm2_t<T, AS, 4>(a, x))

@@ -69,6 +69,8 @@ int launch_moe_gather(const void* x, const int32_t* sorted_pairs, void* xs, int 
                       cudaStream_t stream);
 int launch_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int dtype, cudaStream_t stream);
 int launch_gemm2(const MmArgs& a, const void* x);
+int launch_gemm2_multi(const MmArgs& a, const void* x, int nsets, const void* const* packed, const void* const* scales,
+                       const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* Ns);
 int gemm_gshc(const MmArgs& a);  // 4-bit, CTA-pair (cta_group::2) tier; x already permuted
 int launch_allreduce(void* inout, int n, int dtype, int rank, int world, const void* const* peer_bufs,
                      size_t flag_offset, int max_elems, void* seq, cudaStream_t stream);

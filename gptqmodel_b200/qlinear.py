@@ -30,12 +30,14 @@ from .adapter import Lora
 
 _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
 DECODE_MAX_M = 8
+PREFILL_MIN_M = 128  # M > 128: the CTA-pair prefill tier (b2q_gemm_multi serves sibling groups there)
 
 
 class SiblingGroup:
-    """QuantLinears that consume the SAME activations (q/k/v, gate/up) served by ONE decode launch.
+    """QuantLinears that consume the SAME activations (q/k/v, gate/up) served by ONE launch: `b2q_decode_multi` for
+    <= 8 tokens, `b2q_gemm_multi` (persistent prefill tier) for > 128 tokens; 9..128 tokens run per module.
 
-    The first member called with a new `x` launches `b2q_decode_multi` for all members and parks the siblings'
+    The first member called with a new `x` launches for all members and parks the siblings'
     outputs; each sibling's `forward(x)` then just picks its result up.  Every module keeps the reference's
     per-module `forward(x) -> y` contract (same arithmetic; bit-identical to separate calls whenever the fused launch
     splits K like the single launches would, see `b2q_debug_decode_plan`); only the launch count changes.  This is
@@ -83,9 +85,18 @@ class SiblingGroup:
         bias = vp(*[_ptr(m._bias_for(x2.dtype)) for m in mods])
         outp = vp(*[o.data_ptr() for o in outs])
         Ns = (ctypes.c_int * n)(*[m.out_features for m in mods])
-        check(lib.b2q_decode_multi(x2.data_ptr(), n, packed, scales, zeros, _ptr(who.perm), bias, outp, Ns, M, K, who.bits,
-                                   who.group_size, _DTYPE_CODE[x2.dtype],
-                                   torch.cuda.current_stream(x2.device).cuda_stream), "b2q_decode_multi")
+        stream = torch.cuda.current_stream(x2.device).cuda_stream
+        if M <= DECODE_MAX_M:
+            check(lib.b2q_decode_multi(x2.data_ptr(), n, packed, scales, zeros, _ptr(who.perm), bias, outp, Ns, M, K,
+                                       who.bits, who.group_size, _DTYPE_CODE[x2.dtype], stream), "b2q_decode_multi")
+        else:  # prefill tier: one persistent launch over the tile columns of all siblings, x[:, perm] gathered once
+            ws, ws_bytes = None, 0
+            if who.perm is not None:
+                ws_bytes = M * K * 2
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device)
+            check(lib.b2q_gemm_multi(x2.data_ptr(), n, packed, scales, zeros, _ptr(who.perm), bias, outp, Ns, M, K,
+                                     who.bits, who.group_size, _DTYPE_CODE[x2.dtype], _ptr(ws), ws_bytes, stream),
+                  "b2q_gemm_multi")
         self.key = key
         self._x_ref = x2
         self.pending = {id(m): o for m, o in zip(mods, outs) if m is not who}
@@ -322,7 +333,7 @@ class B200KernelMixin:
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         M = x2.shape[0]
-        if self._siblings is not None and 1 <= M <= DECODE_MAX_M:
+        if self._siblings is not None and (1 <= M <= DECODE_MAX_M or M > PREFILL_MIN_M):
             return self._siblings.run(self, x2, M).reshape(out_shape)
         out = torch.empty((M, N), dtype=x.dtype, device=x.device)
         if M == 0:

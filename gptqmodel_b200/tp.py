@@ -225,14 +225,46 @@ class RowParallelLinear(torch.nn.Module):
     a `FusedDecodeAllReduce` -> matmul and all-reduce in one launch when the input has <= 8 tokens.
     """
 
-    def __init__(self, inner: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, reduce=None):
+    def __init__(self, inner: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, reduce=None,
+                 overlap_chunks: int = 4, overlap_min_tokens: int = 1024):
         super().__init__()
         self.inner = inner
         self.group = group
         self.reduce = reduce
+        self.overlap_chunks = overlap_chunks
+        self.overlap_min_tokens = overlap_min_tokens
+        self._side = None
+
+    def _forward_overlapped(self, x2: torch.Tensor) -> torch.Tensor:
+        """Prefill-sized inputs: the token rows are cut into `overlap_chunks` blocks (multiples of the 256-row GEMM tile);
+        the NCCL all-reduce of block c runs on a side stream while the shard's GEMM of block c + 1 runs on the caller's
+        stream, so only the last block's collective is exposed (at TP-8 the 64 un-overlapped 16 MiB all-reduces were ~30 %
+        of the prefill pass).  Fork / join with events: CUDA-graph capturable."""
+        M = x2.shape[0]
+        cs = -(-M // self.overlap_chunks)
+        cs = max(256, (cs + 255) // 256 * 256)
+        cur = torch.cuda.current_stream(x2.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=x2.device)
+        side = self._side
+        parts = []
+        for c0 in range(0, M, cs):
+            yc = self.inner(x2[c0:c0 + cs])
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                dist.all_reduce(yc, op=dist.ReduceOp.SUM, group=self.group)
+            parts.append(yc)  # kept alive until the join below: no allocator reuse while the side stream still reads it
+        cur.wait_stream(side)
+        return torch.cat(parts, dim=0)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         tokens = x.numel() // x.shape[-1]
+        if (self.overlap_chunks > 1 and tokens >= self.overlap_min_tokens and x.is_cuda and dist.is_available()
+                and dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            y = self._forward_overlapped(x.reshape(-1, x.shape[-1]))
+            return y.reshape(x.shape[:-1] + (y.shape[-1],))
         if isinstance(self.reduce, FusedDecodeAllReduce) and 1 <= tokens <= 8 and getattr(self.inner, "perm", 1) is None \
                 and getattr(self.inner, "bits", 0) == 4 and not getattr(self.inner, "adapter", None):
             return self.inner.forward_allreduce(x, self.reduce)

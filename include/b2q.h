@@ -93,6 +93,14 @@ int b2q_decode_multi(const void* x, int nsets, const void* const* packed, const 
                      const int32_t* const* qzeros, const int32_t* perm, const void* const* bias, void* const* out,
                      const int* N, int M, int K, int bits, int group_size, int dtype, void* stream);
 
+/* The same for the prefill tier (bits = 4, M > 128): the 256-feature tile columns of all sets form one index space for the
+ * persistent CTA pairs (q|k|v: 192 tiles instead of 128 + 32 + 32 at M = 2048), one launch instead of nsets, and act-order
+ * siblings gather x[:, perm] ONCE into `workspace` (>= M*K*2 bytes when perm != NULL). */
+int b2q_gemm_multi(const void* x, int nsets, const void* const* packed, const void* const* scales,
+                   const int32_t* const* qzeros, const int32_t* perm, const void* const* bias, void* const* out,
+                   const int* N, int M, int K, int bits, int group_size, int dtype, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- Grouped MoE expert path (BASELINE configs[4]; the reference's unused analogue: swordfish_moe.cu:9-17,38-48) --------
  * y[t] = sum_j w[t, j] * W2_e( silu(W1_e x[t]) * W3_e x[t] ),  e = topk_ids[t, j], in FIVE launches without any host
  * synchronisation (CUDA-graph capturable).  Expert weights are the b2q_prepack'ed tensors of the per-expert QuantLinears

@@ -353,8 +353,11 @@ def test_sibling_fusion_bit_identical(sym, gs, bias):
         # a different input invalidates the parked outputs; calling only one sibling still works
         x2 = (x * 0.5).to(torch.float16)
         assert torch.equal(mods[1](x2), mods[1].__class__.forward(mods[1], x2))
-        big = (torch.randn(64, K, generator=gen) * 0.5).to(torch.float16).to(DEV)   # M > 8: falls through to the GEMM tier
+        big = (torch.randn(64, K, generator=gen) * 0.5).to(torch.float16).to(DEV)   # 9..128: per module (small-batch tier)
         assert_close_rel(mods[0](big), oracle_forward(Ls[0], big.cpu()), 1e-3, "fused M=64")
+        pre = (torch.randn(300, K, generator=gen) * 0.5).to(torch.float16).to(DEV)  # > 128: ONE persistent prefill launch
+        for m_, L_ in zip(mods, Ls):
+            assert_close_rel(m_(pre), oracle_forward(L_, pre.cpu()), 1e-3, "fused prefill M=300")
         for m in mods:
             m._siblings = None
     # refused combinations
@@ -373,7 +376,7 @@ def test_sibling_fusion_with_shared_act_order():
     mods = [_module(L) for L in Ls]
     assert mods[0].perm is not None and fuse_siblings(mods)
     gen = torch.Generator().manual_seed(4)
-    for M in (1, 5):
+    for M in (1, 5, 260):  # decode launch / prefill launch (x[:, perm] gathered once for both siblings)
         x = (torch.randn(M, K, generator=gen) * 0.5).to(torch.float16)
         for m, L in zip(mods, Ls):
             assert_close_rel(m(x.to(DEV)), oracle_forward(L, x), 1e-3, f"act-order fused M={M}")

@@ -20,4 +20,8 @@ def test_tensor_parallel_stack_matches_unsharded_oracle_on_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", "29531",
                         os.path.join(ROOT, "tests", "tp_gpu_worker.py")], capture_output=True, text=True, timeout=400)
-    assert r.returncode == 0 and "TP_OK" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"tp_gpu_worker_w{world}.log"), "w") as f:  # full worker output for diagnosis
+        f.write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+    lines = [ln for ln in (r.stdout + r.stderr).splitlines() if "FAIL" in ln or "Error" in ln or "TP_OK" in ln]
+    assert r.returncode == 0 and "TP_OK" in r.stdout, "\n".join(lines[-12:])

@@ -59,11 +59,17 @@ for sym, gs, bias in ((True, 128, False), (False, 64, True)):
             for rep in range(2):                            # twice: both slots / the sequence counters of our kernels
                 y = layer(h_ref[:, rank * inter // world:(rank + 1) * inter // world].contiguous().to(dev))
             torch.cuda.synchronize()
-            # the row-parallel sum rounds every rank's partial (NCCL / p2p: 16-bit partials) or sums fp32 partials (fused):
-            # compare with the unsharded oracle at 2e-3 (world roundings of partial sums instead of one)
-            assert_close_rel(y, y_ref, 2e-3, f"{name} sym={sym} M={M}")
+            # NCCL / p2p: every rank's partial sum is rounded to 16 bits and the reduction adds `world` of them (NCCL's ring
+            # rounds the running sum at every hop): ~sqrt(2 * world) roundings of 2^-11 instead of one -> 1e-3 * (1 +
+            # sqrt(world) / 2).  The fused launch sums fp32 partials and rounds once: 2e-3 covers its chained oracle.
+            rel = 2e-3 if name == "fused" else 1e-3 * (1.0 + world ** 0.5 / 2)
+            try:
+                assert_close_rel(y, y_ref, rel, f"{name} sym={sym} M={M} world={world}")
+            except AssertionError as e:
+                print(f"[r{rank}] FAIL {e}", flush=True)
+                raise
             o, r = y.float().cpu(), y_ref.float()
-            ratio = float(((o - r).abs() / (2e-3 * r.abs() + 2e-3 * r.pow(2).mean().sqrt())).max())
+            ratio = float(((o - r).abs() / (rel * r.abs() + rel * r.pow(2).mean().sqrt())).max())
             worst[name] = max(worst.get(name, 0.0), ratio)
 torch.cuda.synchronize()
 dist.barrier()
