@@ -192,7 +192,7 @@ def _row_parallel(mod, x, world):
     return rp(x)
 
 
-OVERLAP_CHUNKS = 4
+OVERLAP_CHUNKS = 1
 
 
 def _all_reduce(t):
@@ -533,8 +533,9 @@ def main():
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="keep NCCL for the small decode all-reduces (default: b2q_allreduce, our one-shot kernel over "
                          "NVLink peer memory; measured 715 vs 605 tok/s at TP-4)")
-    ap.add_argument("--overlap-chunks", type=int, default=4,
-                    help="N > 1 prefill: token blocks whose all-reduce overlaps the next block's GEMM (1 = off)")
+    ap.add_argument("--overlap-chunks", type=int, default=1,
+                    help="N > 1 prefill: token blocks whose all-reduce overlaps the next block's GEMM (default 1 = off: "
+                         "measured SLOWER at TP-4, 17.5 vs 12.3 ms per pass, profiles/r02_tp_notes.md)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinear (224/step) instead of fusing q/k/v and gate/up")
     ap.add_argument("--decode-v2", action="store_true",
                     help="EXPERIMENTAL: decode tier v2 (b2q_decode2.cu; sets B2Q_DECODE_V2=1), result marked experimental")

@@ -226,7 +226,7 @@ class RowParallelLinear(torch.nn.Module):
     """
 
     def __init__(self, inner: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, reduce=None,
-                 overlap_chunks: int = 4, overlap_min_tokens: int = 1024):
+                 overlap_chunks: int = 1, overlap_min_tokens: int = 1024):
         super().__init__()
         self.inner = inner
         self.group = group
@@ -238,8 +238,10 @@ class RowParallelLinear(torch.nn.Module):
     def _forward_overlapped(self, x2: torch.Tensor) -> torch.Tensor:
         """Prefill-sized inputs: the token rows are cut into `overlap_chunks` blocks (multiples of the 256-row GEMM tile);
         the NCCL all-reduce of block c runs on a side stream while the shard's GEMM of block c + 1 runs on the caller's
-        stream, so only the last block's collective is exposed (at TP-8 the 64 un-overlapped 16 MiB all-reduces were ~30 %
-        of the prefill pass).  Fork / join with events: CUDA-graph capturable."""
+        stream, so only the last block's collective is exposed.  Fork / join with events: CUDA-graph capturable.  OPT-IN
+        (`overlap_chunks` > 1): measured at TP-4 it is SLOWER than one GEMM + one all-reduce (17.5 vs 12.3 ms per 2048-token
+        pass: the quarter-size GEMMs fill the 74 CTA pairs worse, NCCL competes for SMs with the GEMM it overlaps, and the
+        blocks are concatenated afterwards) — profiles/r02_tp_notes.md."""
         M = x2.shape[0]
         cs = -(-M // self.overlap_chunks)
         cs = max(256, (cs + 255) // 256 * 256)

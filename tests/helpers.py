@@ -91,6 +91,29 @@ def ref_rounding_slack(W, x, sigmas=4.0):
     return sigmas * sigma * torch.sqrt((x.detach().float().cpu() ** 2) @ (W.detach().float().cpu() ** 2))
 
 
+def scale_once_tier(layer, M):
+    """True when b2q_mm serves (layer, M tokens) with a tier that applies the scale once per group to an exact integer dot
+    product (decode tier: 4-bit, M <= 8, K % 128 == 0, group 64 / 128 / per-channel; 8-bit GEMV at M == 1) instead of feeding
+    the tensor cores the reference's per-weight rounded operand."""
+    K, gs, bits = layer["K"], layer["group_size"], layer["bits"]
+    if bits == 4:
+        return M <= 8 and K % 128 == 0 and gs in (64, 128, -1, K)
+    return M == 1 and K % 128 == 0
+
+
+def assert_layer_close(out, layer, x, rel=1e-3, what=""):
+    """Module output against the oracle of the same checkpoint tensors: 1e-3 for the exact-operand tiers, 1e-3 plus the
+    reference's own weight-rounding noise (ref_rounding_slack) for the scale-once tiers — see tests/test_awq.py."""
+    xc = x.detach().cpu()
+    ref = oracle_forward(layer, xc)
+    slack = None
+    if scale_once_tier(layer, xc.reshape(-1, xc.shape[-1]).shape[0]):
+        W = oracle.dequantize_weight(layer["qweight"].cpu(), layer["qzeros"].cpu(), layer["scales"].cpu().to(xc.dtype),
+                                     layer["g_idx"].cpu(), layer["bits"])
+        slack = ref_rounding_slack(W, xc.reshape(-1, xc.shape[-1])).reshape(ref.shape)
+    assert_close_rel(out, ref, rel, what, slack=slack)
+
+
 def assert_close_rel(out, ref, rel=1e-3, what="", slack=None):
     """|out - ref| <= rel * |ref| + rel * rms(ref) (+ slack): the north-star's "1e-3 rel fp16" with an absolute floor
     for outputs that cancel to ~0.  `slack` ([M, N] or scalar, absolute): see ref_rounding_slack()."""

@@ -45,10 +45,12 @@ def test_awq_full_size_layers_on_gpu(K, N, gs):
     qz = torch.randint(-(2 ** 31), 2 ** 31 - 1, (K // gs, N // 8), dtype=torch.int32, device="cuda", generator=gen)
     sc = (torch.rand(K // gs, N, device="cuda", generator=gen) * 0.01 + 0.005).to(torch.float16)
     m = B200AwqQuantLinear.from_awq_tensors(qw, qz, sc, gs)
+    W = oracle.awq_dequantize(qw.cpu(), qz.cpu(), sc.cpu(), gs)
     for M in (1, 7, 64, 300):
         x = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).to(torch.float16)
         ref = oracle.awq_forward(x.cpu(), qw.cpu(), qz.cpu(), sc.cpu(), gs)
-        assert_close_rel(m(x), ref, 1e-3, f"awq K={K} N={N} M={M}")
+        # M <= 8 runs on the decode tier (scale applied once per group): + the reference's own weight-rounding noise
+        assert_close_rel(m(x), ref, 1e-3, f"awq K={K} N={N} M={M}", slack=ref_rounding_slack(W, x.cpu()) if M <= 8 else None)
 
 
 @pytest.mark.gpu
@@ -61,8 +63,9 @@ def test_loaded_checkpoint_runs_on_gpu(tmp_path):
     _write(str(tmp_path), {n: _ckpt_tensors(L) for n, L in layers.items()}, cfg)
     mods = loader.load_quantized_linears(str(tmp_path), device="cuda")
     x = (torch.randn(5, 512) * 0.5).to(torch.float16)
+    from helpers import assert_layer_close
     for n, L in layers.items():
-        assert_close_rel(mods[n](x.cuda()), oracle_forward(L, x), 1e-3, n)
+        assert_layer_close(mods[n](x.cuda()), L, x, 1e-3, n)
 
 
 @pytest.mark.gpu

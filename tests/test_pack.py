@@ -67,3 +67,27 @@ def test_module_pack_block_fills_reference_tensors(ref_cases, name):
     if m["bias"]:
         assert torch.equal(mod.bias.data, ref_cases.get(name, "bias"))
     assert mod.qzero_format() == 2 and set(mod.state_dict()) >= {"qweight", "qzeros", "scales", "g_idx"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(META))
+def test_pack_gptq_on_the_gpu_bit_exact_vs_reference(ref_cases, name):
+    # the quantiser-side contract on the device (the reference's pack_gpu, qlinear/__init__.py:1326-1498): same integer ops
+    # on CUDA tensors must give the tensors the reference's CPU packers produced, and the packed module must then run
+    m = ref_cases.meta[name]
+    dev = "cuda"
+    bias = ref_cases.get(name, "lin_bias").to(dev) if m["bias"] else None
+    out = pack_gptq(ref_cases.get(name, "weight").to(dev), ref_cases.get(name, "in_scales").to(dev),
+                    ref_cases.get(name, "in_zeros").to(dev), ref_cases.get(name, "g_idx").to(dev), m["bits"], bias=bias)
+    for k in ("qweight", "qzeros", "scales", "g_idx"):
+        assert out[k].is_cuda and torch.equal(out[k].cpu(), ref_cases.get(name, k)), k
+    if m["K"] % 64 == 0 and m["N"] % 32 == 0:
+        from gptqmodel_b200 import B200QuantLinear
+        from helpers import assert_close_rel
+        mod = B200QuantLinear.from_checkpoint_tensors(out["qweight"], out["qzeros"], out["scales"], out["g_idx"], m["bits"],
+                                                      m["group_size"], bias=out.get("bias"), desc_act=m["desc_act"],
+                                                      sym=m["sym"])
+        x = ref_cases.get(name, "x")
+        ref = oracle.forward(x, ref_cases.get(name, "qweight"), ref_cases.get(name, "qzeros"), ref_cases.get(name, "scales"),
+                             ref_cases.get(name, "g_idx"), m["bits"], bias=ref_cases.get(name, "bias"))
+        assert_close_rel(mod(x.to(dev)), ref, 1e-3, f"packed on the GPU: {name}")
