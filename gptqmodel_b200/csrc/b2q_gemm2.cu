@@ -298,8 +298,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_fullA + 8 * s, 1);
-      mbar_init(bar_bready + 8 * s, 2);
+      // ONE "operands ready" barrier per stage (leader-owned): the activation producer's arrive.expect_tx (both CTAs' TMA
+      // halves complete_tx on it) + one arrive per CTA when its 128 feature rows are dequantised.  The MMA issuer waits
+      // once per k-block instead of twice (its issue loop, not the tensor pipe, sets the k-block time: r02_midm_notes.md).
+      mbar_init(bar_fullA + 8 * s, 3);
+      mbar_init(bar_bready + 8 * s, 1);  // (unused)
       mbar_init(bar_fullP + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -387,7 +390,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
           const int s = kbc % STAGES;
           const uint32_t ph = (kbc / STAGES) & 1;
           mbar_wait(bar_fullA + 8 * s, ph);
-          mbar_wait(bar_bready + 8 * s, ph);
           tc_fence_after();
           if (lane == 0) {
             const uint64_t adesc = umma_desc_k_sw128(sA + s * G2_A_BYTES);
@@ -416,7 +418,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2P_THREADS, 1)
     f[1] = f[0] + 8;
     f[2] = f[0] + 64;
     f[3] = f[0] + 72;
-    const uint32_t bready_leader = mapa_u32(bar_bready, 0);
+    const uint32_t bready_leader = mapa_u32(bar_fullA, 0);  // the leader's operands-ready barrier
     int kbc = 0;
     for (int tile = pair; tile < ntiles_total; tile += npairs) {
       for (int kb = 0; kb < nkb; ++kb, ++kbc) {
