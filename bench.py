@@ -50,7 +50,7 @@ def load_peaks():
 
 def load_traffic():
     """DRAM bytes measured by ncu (--set full) for one decode launch, as a ratio of its algorithmic bytes."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(p):
         return json.load(open(p))
     return None
@@ -302,7 +302,10 @@ class CpuArm:
         best = (None, 1e30)
         for c in cands:
             torch.set_num_threads(c)
-            self.step()
+            first = self.step()
+            if first > 20 * best[1]:  # oversubscribed (measured: 0.8 ms per layer at 64 threads, 480 ms at 128): stop here
+                self.thread_table[c] = round(first * 1e3, 3)
+                break
             ts = sorted(self.step() for _ in range(iters))
             med = ts[len(ts) // 2]
             self.thread_table[c] = round(med * 1e3, 3)
@@ -728,7 +731,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
                 "traffic": None if args.decode_v2 else traffic,  # the ncu capture is of the default kernel
                 "traffic_note": "average per launch = measured DRAM/algorithmic ratio of the ncu --set full capture "
-                                "(profiles/r01_decode_final.txt: 30,318,080 B DRAM vs 30,539,776 B algorithmic for the "
+                                "(profiles/r02_decode_ncu.txt: 30,317,568 B DRAM vs 30,539,776 B algorithmic for the "
                                 "4096x14336 launch) x algorithmic bytes per launch",
             },
             "prefill": {
@@ -738,7 +741,10 @@ def main():
                              "achieved": tflops / world, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                              "frac": tflops / world / peaks["tflops_sustained"],
                              "peak_note": "sustained cuBLAS bf16 (kernel timed inside a long step); burst peak "
-                                          f"{peaks['tflops_burst']}", "traffic": None},
+                                          f"{peaks['tflops_burst']}",
+                             "traffic": (tr or {}).get("gemm2p_kernel", {}).get("dram_bytes"),
+                             "traffic_note": "DRAM bytes of ONE 4096x4096 M=2048 launch (ncu --set full, "
+                                             "profiles/r02_gemm2p_ncu.txt); tensor-bound kernel"},
                 "e2e_ms_per_pass": pre_e2e_ms,
                 "e2e_tokens_per_s": Mp / (pre_e2e_ms * 1e-3),
             },
