@@ -59,4 +59,13 @@ for M in (1, 6):
     for m, L in zip(ms, Ls):
         assert_close_rel(m(x.cuda()), oracle_forward(L, x), 1e-3, f"fused M={M}")
     print("ok fused siblings M =", M, flush=True)
+# sibling-fused PREFILL launch (b2q_gemm_multi), incl. act-order siblings that share one gather of x
+for desc in (False, True):
+    Ls = [make_layer(512, n, group_size=64, sym=False, desc_act=desc, bias=True, seed=33) for n in (512, 96, 288)]
+    ms = [mod(L) for L in Ls]
+    assert fuse_siblings(ms)
+    x = (torch.randn(300, 512, generator=torch.Generator().manual_seed(9)) * 0.5).to(torch.float16)
+    for m, L in zip(ms, Ls):
+        assert_close_rel(m(x.cuda()), oracle_forward(L, x), 1e-3, f"fused prefill act-order={desc}")
+    print("ok fused prefill siblings, act-order =", desc, flush=True)
 print("all ok")
