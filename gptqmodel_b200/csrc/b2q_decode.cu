@@ -29,7 +29,7 @@ template <typename T, bool ASYM, bool G64>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     decode_kernel(const __grid_constant__ DecSets S, const int32_t* __restrict__ perm, const T* __restrict__ x, int M,
                   int K, int gsh, int qpc, int max_tiles, int ngroups, int stl,
-                  unsigned long long* __restrict__ trace) {
+                  const __grid_constant__ DecodeAR ar, unsigned long long* __restrict__ trace) {
   using E = ET<T>;
   extern __shared__ __align__(128) uint8_t dsm[];
   // optional phase timestamps (debug): trace[blockIdx.x * 16 + slot] = %globaltimer (ns)
@@ -216,6 +216,9 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const uint32_t xf_a0 = smem_u32(sx) + (uint32_t)((g * kspan + t * 16 + wg * 128) * 2);
   const uint32_t xs_a0 = smem_u32(xsum) + (uint32_t)((2 * t + wg * 16) * 4);
   const uint32_t xf_qstep = (uint32_t)gw * 256u, xs_qstep = (uint32_t)gw * 64u;
+  // fused all-reduce: the sequence number of this call (advanced by the previous launch's last CTA)
+  uint32_t ar_seq = 0;
+  if (ar.world > 1) ar_seq = *reinterpret_cast<const volatile uint32_t*>(ar.ctl);
   int u = 0;
   for (int ti = 0; ti < ntiles; ++ti) {
     const TileRef<T> tr = resolve_tile<T>(S, tile0 + ti * C);
@@ -321,16 +324,65 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         const int m = 2 * (ln & 3) + (acc & 1);
         if (m < M) {
           const int n = nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
-          // reference order: round the matmul to the output dtype, then add bias (qlinear/torch.py:337-342)
-          T o = E::from_f(v);
-          if (bias != nullptr) o = E::from_f(E::to_f(o) + E::to_f(bias[n]));
-          out[(size_t)m * N + n] = o;
+          if (ar.world > 1) {
+            // row-parallel shard + all-reduce in this launch (launch_decode_allreduce: one tile per CTA, no split-K): the
+            // fp32 partial sum goes into slot (seq & 1), row `rank`, of EVERY rank's symmetric buffer; the bias of a
+            // row-parallel layer lives on one rank only and joins that rank's partial
+            if (bias != nullptr) v += E::to_f(bias[n]);
+            const size_t o = ((size_t)(ar_seq & 1u) * ar.world + ar.rank) * (size_t)ar.max_elems + (size_t)m * N + n;
+            for (int p = 0; p < ar.world; ++p) reinterpret_cast<float*>(ar.buf[p])[o] = v;
+          } else {
+            // reference order: round the matmul to the output dtype, then add bias (qlinear/torch.py:337-342)
+            T o = E::from_f(v);
+            if (bias != nullptr) o = E::from_f(E::to_f(o) + E::to_f(bias[n]));
+            out[(size_t)m * N + n] = o;
+          }
         }
       }
     }
     if (ti < 5) stamp(5 + 2 * ti);
   }
   stamp(15);
+
+  // ---- 3b. fused all-reduce across GPUs (same protocol as decode2_kernel; one tile per CTA, nrank == 1) ------------
+  if (ar.world > 1) {
+    __threadfence_system();  // the pushed partial sums are visible system-wide before the flag
+    __syncthreads();
+    const int cta = (int)blockIdx.x;
+    if ((int)threadIdx.x < ar.world) {
+      const int p = threadIdx.x;
+      uint32_t* peer_flags = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ar.buf[p]) + ar.flag_offset);
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags + ar.rank * 160 + cta), "r"(ar_seq + 1u)
+                   : "memory");
+      const uint32_t* my_flags =
+          reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ar.buf[ar.rank]) + ar.flag_offset);
+      if (!spin_until_geq_sys(my_flags + p * 160 + cta, ar_seq + 1u)) ar.ctl[2] = 1u + (uint32_t)p;  // dead peer
+    }
+    __syncthreads();
+    if (ntiles > 0) {
+      const TileRef<T> tr = resolve_tile<T>(S, tile0);
+      const float* mine = reinterpret_cast<const float*>(ar.buf[ar.rank]) + (size_t)(ar_seq & 1u) * ar.world * ar.max_elems;
+      for (int i = wg * 32 + lane; i < 256; i += gw * 32) {
+        const int acc = i >> 5, ln = i & 31;
+        const int m = 2 * (ln & 3) + (acc & 1);
+        if (m < M) {
+          const int n = tr.nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
+          float v = 0.f;
+          for (int p = 0; p < ar.world; ++p) v += __ldcg(mine + (size_t)p * ar.max_elems + (size_t)m * tr.N + n);
+          tr.out[(size_t)m * tr.N + n] = E::from_f(v);  // summed in rank order: identical on every rank
+        }
+      }
+    }
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned total = gridDim.x * gridDim.y;
+      if (atomicAdd(ar.ctl + 1, 1u) == total - 1u) {  // every CTA has read seq: the last one advances it
+        ar.ctl[1] = 0u;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(ar.ctl) = ar_seq + 1u;
+      }
+    }
+  }
 
   // ---- 4. split-K: the cluster ranks share the tiles of the final DSMEM reduction -----------------
   if (nrank > 1) {
@@ -431,7 +483,7 @@ bool decode_plan(int version, const MmArgs& a, int NT, int* out8) {
 }
 
 template <typename T, bool ASYM, bool G64>
-static int launch_decode_t(const MmArgs& a, const DecSets& sets, const DecodeCfg& c) {
+static int launch_decode_t(const MmArgs& a, const DecSets& sets, const DecodeCfg& c, const DecodeAR& ar) {
   auto kern = decode_kernel<T, ASYM, G64>;
   if (c.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
@@ -455,7 +507,7 @@ static int launch_decode_t(const MmArgs& a, const DecSets& sets, const DecodeCfg
   if (a.group_size == 64) gsh = 0;
   else if (a.group_size == 128) gsh = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, sets, a.perm, (const T*)a.x, a.M, a.K, gsh, c.qpc, c.max_tiles,
-                                     c.ngroups, c.stl, (unsigned long long*)g_trace_ptr);
+                                     c.ngroups, c.stl, ar, (unsigned long long*)g_trace_ptr);
   return (int)e;
 }
 
@@ -492,11 +544,32 @@ static int launch_decode_sets(const MmArgs& a, const DecSets& sets) {
     return -1;
   }
   const bool asym = a.qzeros != nullptr, g64 = a.group_size == 64;
+  const DecodeAR none = {};
 #define B2Q_DEC_CASE(T)                                                          \
-  (asym ? (g64 ? launch_decode_t<T, true, true>(a, sets, c)                      \
-               : launch_decode_t<T, true, false>(a, sets, c))                    \
-        : (g64 ? launch_decode_t<T, false, true>(a, sets, c)                     \
-               : launch_decode_t<T, false, false>(a, sets, c)))
+  (asym ? (g64 ? launch_decode_t<T, true, true>(a, sets, c, none)                \
+               : launch_decode_t<T, true, false>(a, sets, c, none))              \
+        : (g64 ? launch_decode_t<T, false, true>(a, sets, c, none)               \
+               : launch_decode_t<T, false, false>(a, sets, c, none)))
+  return a.dtype == 0 ? B2Q_DEC_CASE(__half) : B2Q_DEC_CASE(__nv_bfloat16);
+#undef B2Q_DEC_CASE
+}
+
+// Row-parallel shard + all-reduce on decode_kernel: only for launches in which every CTA owns at most ONE tile and K is not
+// split (o_proj / down_proj of a 4096-wide model at any TP degree: 128 tiles) — where decode_kernel is the faster of the
+// two decode kernels; everything else takes decode2_kernel's epilogue.  -2 = not applicable.
+int launch_decode1_allreduce(const MmArgs& a, const DecSets& sets, const DecodeAR& ar) {
+  const int NT = sets.tile_end[sets.nsets - 1];
+  if (NT > 148 || a.perm != nullptr) return -2;
+  MmArgs a1 = a;
+  a1.tune_ks = 1;
+  DecodeCfg c;
+  if (!decode_config(a1, NT, c) || c.ks != 1 || c.ngroups != 1 || c.C < NT || c.C > 160) return -2;
+  const bool asym = a.qzeros != nullptr, g64 = a.group_size == 64;
+#define B2Q_DEC_CASE(T)                                                          \
+  (asym ? (g64 ? launch_decode_t<T, true, true>(a1, sets, c, ar)                 \
+               : launch_decode_t<T, true, false>(a1, sets, c, ar))               \
+        : (g64 ? launch_decode_t<T, false, true>(a1, sets, c, ar)                \
+               : launch_decode_t<T, false, false>(a1, sets, c, ar)))
   return a.dtype == 0 ? B2Q_DEC_CASE(__half) : B2Q_DEC_CASE(__nv_bfloat16);
 #undef B2Q_DEC_CASE
 }

@@ -25,6 +25,7 @@
 namespace b2q {
 
 constexpr int DEC_AR_MAXCTA = 160;  // flag columns per source rank (>= CTAs of one launch: 148)
+int launch_decode1_allreduce(const MmArgs& a, const DecSets& sets, const DecodeAR& ar);  // b2q_decode.cu
 
 // Cluster barrier whose memory ordering is only CTA-scope: every cluster-scope release compiles to MEMBAR.ALL.GPU on
 // sm_100a (checked with cuobjdump), which waits on the whole memory system although the data exchanged here lives in
@@ -584,6 +585,11 @@ int launch_decode_allreduce(const MmArgs& a, const DecodeAR& ar) {
   sets.qzeros[0] = (const uint32_t*)a.qzeros;
   sets.bias[0] = a.bias;
   sets.out[0] = a.out;
+  // single-tile launches run faster on decode_kernel (b2q_decode.cu), which carries the same epilogue for that case
+  if (env().decode_v2 != 1) {
+    const int rc1 = launch_decode1_allreduce(a, sets, ar);
+    if (rc1 != -2) return rc1;
+  }
   const int rc = launch_decode2_ar(a, sets, ar);
   if (rc == -2) {
     set_error("b2q_decode_allreduce: no launch plan fits shared memory for M=%d K=%d N=%d", a.M, a.K, a.N);
