@@ -248,6 +248,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
         umma_commit(bar_wempty + 8 * ws);  // the dequantised stage may be overwritten
         umma_commit(bar_xempty + 8 * xs);  // the x tile has been read
         if (i + nissue >= NI) umma_commit(bar_tfull);  // this issuer's last block
+        // wready(i) completed => the dequant group has read packed stage i % PST: stream block i + PST into it (one
+        // issuer thread per k-block class, off the dequant groups' latency chain)
+        if (i + PST < NI) load_weights(i + PST, i % PST);
       }
       __syncwarp();
     }
@@ -297,9 +300,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
             zh[u] = (int)((zwh >> (4 * g)) & 15u);
           }
         }
-        // codes + scales are in registers: once the whole group has read, its leader refills the stage for block i + PST
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + gq), "r"(TG) : "memory");
-        if (tl == 0 && i + PST < NI) load_weights(i + PST, s);
+        // (the packed stage is refilled for block i + PST by the MMA issuer of block i: it observes wready(i), which this
+        //  group only signals after every thread has read the stage — no barrier or copy issue inside this chain)
         if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);  // the MMA of block i - WST has read the stage
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -348,8 +350,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
             for (int h = 0; h < 2; ++h) pvs[r][j][h] = pj[((fr >> 5) * 2 + h) * 32 + (fr & 31)];
           }
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + gq), "r"(TG) : "memory");  // codes are in registers: refill the stage
-        if (tl == 0 && i + PST < NI) load_weights(i + PST, s);
+        // (refilled by the MMA issuer of block i, see the 4-bit path)
         if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -555,8 +556,8 @@ int launch_midm(const MmArgs& a, const void* x) {
   // (profiles/r02_midm_notes.md).  8 dequantised stages = two per group; 4-8 packed stages (refilled by the group's own
   // leader); 4-8 activation stages in their own ring.
 #define B2Q_MM_NTOK(T, BITS, AS)                                                                  \
-  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, 8, 8>(a, x, ks)                                   \
-   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, 8, 8>(a, x, ks)                                   \
+  (a.M <= 16   ? launch_midm_t<T, BITS, AS, 16, (BITS == 4 ? 12 : 8), 8>(a, x, ks)                \
+   : a.M <= 32 ? launch_midm_t<T, BITS, AS, 32, (BITS == 4 ? 12 : 8), 8>(a, x, ks)                \
    : a.M <= 64 ? launch_midm_t<T, BITS, AS, 64, (BITS == 4 ? 8 : 4), 8>(a, x, ks)                 \
                : launch_midm_t<T, BITS, AS, 128, 4, 8>(a, x, ks))
 #define B2Q_MM_CASE(T)                                                          \
@@ -604,8 +605,8 @@ int launch_midm_grouped(int mode, const MmArgs& a, const MoeGroupedArgs& g) {
   while (ks > 1 && (ks - 1) * ((nkb + ks - 1) / ks) >= nkb) ks >>= 1;
   const bool asym = a.qzeros != nullptr;
 #define B2Q_MG_NTOK(T, AS, MODE)                                                             \
-  (ntok == 16   ? launch_midm_t<T, 4, AS, 16, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
-   : ntok == 32 ? launch_midm_t<T, 4, AS, 32, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
+  (ntok == 16   ? launch_midm_t<T, 4, AS, 16, 12, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)    \
+   : ntok == 32 ? launch_midm_t<T, 4, AS, 32, 12, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)    \
    : ntok == 64 ? launch_midm_t<T, 4, AS, 64, 8, 8, MODE>(a, a.x, ks, G, g.rows, grid_z)     \
                 : launch_midm_t<T, 4, AS, 128, 4, 8, MODE>(a, a.x, ks, G, g.rows, grid_z))
 #define B2Q_MG_CASE(T)                                                                       \

@@ -7,11 +7,13 @@ timeout 200 python __graft_entry__.py smoke > gpurun_out/fin_smoke.log 2>&1; ech
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/fin_tests.log 2>&1
 cp gpurun_out/parity.json gpurun_out/fin_parity.json 2>/dev/null
 timeout 500 compute-sanitizer --tool memcheck --print-limit 10 python tools/san_one.py > gpurun_out/fin_san_one_memcheck.log 2>&1
+timeout 200 python tools/microbench.py midm 16 128 > gpurun_out/fin_midm_bench.log 2>&1
 timeout 300 python tools/stress.py 150 > gpurun_out/fin_stress.log 2>&1; echo "rc=$?" >> gpurun_out/fin_stress.log
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"decode|gemm2p|midm|allreduce|gemv_kernel|gemm_kernel" -c 520 --csv --log-file gpurun_out/r02_launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra --no-competitors > gpurun_out/fin_ncu_bench.log 2>&1
 timeout 900 python bench.py > gpurun_out/fin_bench.json 2> gpurun_out/fin_bench.err
 timeout 300 python bench.py --impl reference > gpurun_out/fin_bench_ref.json 2> gpurun_out/fin_bench_ref.err
 for f in gpurun_out/fin_smoke.log gpurun_out/fin_tests.log gpurun_out/fin_san_one_memcheck.log gpurun_out/fin_stress.log; do echo "## $f: $(tail -2 $f | tr '\n' ' ' | cut -c1-200)"; done
+grep "MIDM bits=4 g=128" gpurun_out/fin_midm_bench.log | cut -c1-200
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/fin_bench.json").read().strip().splitlines()[-1])
