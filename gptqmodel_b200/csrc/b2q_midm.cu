@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
   constexpr int XST = C::XST;
+  constexpr bool ISSUER_REFILL = PST >= 3 * DQG;  // who refills the packed stages (see the dequant warps)
   const uint32_t sW = smem_base;                      // [WST][128 features][64 k]      (also: fp32 partial tile)
   const uint32_t sXr = sW + WST * C::W_BYTES;         // [XST] x tile [NTOK][64 k]
   const uint32_t sPr = sXr + XST * C::X_BYTES;        // [PST]{ packed codes | scale / zero rows }
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
         if (i + nissue >= NI) umma_commit(bar_tfull);  // this issuer's last block
         // wready(i) completed => the dequant group has read packed stage i % PST: stream block i + PST into it (one
         // issuer thread per k-block class, off the dequant groups' latency chain)
-        if (i + PST < NI) load_weights(i + PST, i % PST);
+        if (ISSUER_REFILL && i + PST < NI) load_weights(i + PST, i % PST);
       }
       __syncwarp();
     }
@@ -300,8 +301,15 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
             zh[u] = (int)((zwh >> (4 * g)) & 15u);
           }
         }
-        // (the packed stage is refilled for block i + PST by the MMA issuer of block i: it observes wready(i), which this
-        //  group only signals after every thread has read the stage — no barrier or copy issue inside this chain)
+        // Refill of the packed stage for block i + PST.  With >= 3 packed stages per group the MMA issuer of block i does it
+        // (it observes wready(i), which this group only signals after every thread has read the stage: no barrier or copy
+        // issue inside this chain; 7.7 -> 7.5 us at M = 16).  With 1-2 stages per group that is too late — the group would
+        // wait a full HBM round trip per block (M = 128: 10.7 -> 12.3 us measured) — so the group's leader refills right
+        // after the whole group has read.
+        if (!ISSUER_REFILL) {
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + gq), "r"(TG) : "memory");
+          if (tl == 0 && i + PST < NI) load_weights(i + PST, s);
+        }
         if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);  // the MMA of block i - WST has read the stage
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -350,7 +358,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
             for (int h = 0; h < 2; ++h) pvs[r][j][h] = pj[((fr >> 5) * 2 + h) * 32 + (fr & 31)];
           }
         }
-        // (refilled by the MMA issuer of block i, see the 4-bit path)
+        if (!ISSUER_REFILL) {  // see the 4-bit path
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + gq), "r"(TG) : "memory");
+          if (tl == 0 && i + PST < NI) load_weights(i + PST, s);
+        }
         if (i >= WST) mbar_wait(bar_wempty + 8 * ws, ((i / WST) & 1) ^ 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
