@@ -737,7 +737,7 @@ def main():
             "prefill": {
                 "tokens": Mp, "ms_per_pass": ms_pre, "tflops": tflops, "iters": it_pre,
                 "tokens_per_s": Mp / (ms_pre * 1e-3),
-                "roofline": {"kernel": "gemm_kernel (tcgen05 + TMA, TMEM accumulators)", "bound": "tensor",
+                "roofline": {"kernel": "gemm2p_kernel (persistent CTA pairs, tcgen05.mma.cta_group::2 + TMA, TMEM accumulators)", "bound": "tensor",
                              "achieved": tflops / world, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                              "frac": tflops / world / peaks["tflops_sustained"],
                              "peak_note": "sustained cuBLAS bf16 (kernel timed inside a long step); burst peak "
