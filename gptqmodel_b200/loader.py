@@ -40,7 +40,7 @@ class QuantSpec:
     group_size: int = 128
     desc_act: bool = False
     sym: bool = True
-    format: str = "gptq"   # "gptq" (v1 zero-points) | "gptq_v2" | "gemm" (AWQ)
+    format: str = "gptq"   # "gptq" (v1 zero-points) | "gptq_v2" | "gptq_p" (planar, v2 zero-points) | "gemm" (AWQ)
     method: str = "gptq"   # "gptq" | "awq"
     lm_head: bool = False
     dynamic: Optional[Dict[str, dict]] = None
@@ -93,8 +93,8 @@ def parse_quant_config(raw: dict) -> QuantSpec:
         raise NotImplementedError(f"pack_dtype `{pack_dtype}` is not supported (int32 words only, like Marlin / Swordfish)")
     if spec.method not in ("gptq", "awq"):
         raise NotImplementedError(f"quantisation method `{spec.method}` is outside this package (gptq, awq)")
-    if spec.method == "gptq" and spec.format not in ("gptq", "gptq_v2"):
-        raise NotImplementedError(f"GPTQ checkpoint format `{spec.format}` is not supported (gptq, gptq_v2)")
+    if spec.method == "gptq" and spec.format not in ("gptq", "gptq_v2", "gptq_p"):
+        raise NotImplementedError(f"GPTQ checkpoint format `{spec.format}` is not supported (gptq, gptq_v2, gptq_p)")
     if spec.method == "awq" and spec.format != "gemm":
         raise NotImplementedError(f"AWQ checkpoint format `{spec.format}` is not supported (gemm)")
     return spec
@@ -205,7 +205,7 @@ def load_quantized_linears(path: str, device="cuda", dtype: Optional[torch.dtype
                     g_idx = (torch.arange(K, dtype=torch.int32) // gs)
                 m = B200QuantLinear(bits=ms.bits, group_size=ms.group_size, desc_act=ms.desc_act, sym=ms.sym, in_features=K,
                                     out_features=N, bias=t["bias"] is not None, register_buffers=False, dtype=dtype,
-                                    name=prefix)
+                                    name=prefix, format=ms.format)
                 m.qweight, m.qzeros, m.scales = mk(t["qweight"]), mk(t["qzeros"]), mk(t["scales"])
                 m.g_idx, m.bias = mk(g_idx.to(torch.int32)), mk(t["bias"])
                 if ms.format == "gptq":

@@ -22,7 +22,7 @@ class FusedGateUpSilu(torch.nn.Module):
     def __init__(self, gate: B200KernelMixin, up: B200KernelMixin):
         super().__init__()
         for m in (gate, up):
-            if not isinstance(m, B200KernelMixin) or not m._prepacked or m.bits != 4 or m.perm is not None \
+            if not isinstance(m, B200KernelMixin) or not m._prepacked or m.bits != 4 or m.perm is not None or m._gather is not None \
                     or m.bias is not None or m.adapter:
                 raise NotImplementedError("FusedGateUpSilu: post_init'ed 4-bit B200 QuantLinears without act-order, bias "
                                           "or adapter")

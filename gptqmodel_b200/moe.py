@@ -70,7 +70,7 @@ class MoEExperts(torch.nn.Module):
         for mods in (self.w1, self.w3, self.w2):
             m0 = mods[0]
             for m in mods:
-                if not isinstance(m, B200KernelMixin) or not m._prepacked or m.bits != 4 or m.perm is not None \
+                if not isinstance(m, B200KernelMixin) or not m._prepacked or m.bits != 4 or m.perm is not None or m._gather is not None \
                         or m.bias is not None or m.adapter:
                     return None
                 if (m.in_features, m.out_features, m.group_size, m.packed.device, m.scales.dtype) != (

@@ -25,6 +25,7 @@ import torch.nn as nn
 
 import ctypes
 
+from . import layouts
 from ._lib import B2QError, check, lib
 from .adapter import Lora
 
@@ -88,14 +89,14 @@ class SiblingGroup:
         stream = torch.cuda.current_stream(x2.device).cuda_stream
         if M <= DECODE_MAX_M:
             check(lib.b2q_decode_multi(x2.data_ptr(), n, packed, scales, zeros, _ptr(who.perm), bias, outp, Ns, M, K,
-                                       who.bits, who.group_size, _DTYPE_CODE[x2.dtype], stream), "b2q_decode_multi")
+                                       who.kbits, who._kgs, _DTYPE_CODE[x2.dtype], stream), "b2q_decode_multi")
         else:  # prefill tier: one persistent launch over the tile columns of all siblings, x[:, perm] gathered once
             ws, ws_bytes = None, 0
             if who.perm is not None:
                 ws_bytes = M * K * 2
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device)
             check(lib.b2q_gemm_multi(x2.data_ptr(), n, packed, scales, zeros, _ptr(who.perm), bias, outp, Ns, M, K,
-                                     who.bits, who.group_size, _DTYPE_CODE[x2.dtype], _ptr(ws), ws_bytes, stream),
+                                     who.kbits, who._kgs, _DTYPE_CODE[x2.dtype], _ptr(ws), ws_bytes, stream),
                   "b2q_gemm_multi")
         self.key = key
         self._x_ref = x2
@@ -111,16 +112,16 @@ def fuse_siblings(mods) -> bool:
         return False
     m0 = mods[0]
     for m in mods:
-        if not isinstance(m, B200KernelMixin) or not m._prepacked or m.bits != 4:
+        if not isinstance(m, B200KernelMixin) or not m._prepacked or m.kbits != 4 or m._gather is not None:
             return False
         # act-order siblings share a launch only if they share the permutation (q/k/v and gate/up of a GPTQ checkpoint
         # are quantised against the same input Hessian, hence the same g_idx)
         if (m.perm is None) != (m0.perm is None) or (m.perm is not None and not torch.equal(m.perm, m0.perm)):
             return False
-        if (m.in_features, m.group_size, m._is_sym, m.packed.device, m.scales.dtype) != (
-                m0.in_features, m0.group_size, m0._is_sym, m0.packed.device, m0.scales.dtype):
+        if (m.in_features, m._kgs, m._is_sym, m.packed.device, m.scales.dtype) != (
+                m0.in_features, m0._kgs, m0._is_sym, m0.packed.device, m0.scales.dtype):
             return False
-        if m.in_features % 128 != 0 or m.group_size not in (64, 128, m.in_features) or m.adapter:
+        if m.in_features % 128 != 0 or m._kgs not in (64, 128, m.in_features) or m.adapter:
             return False
     grp = SiblingGroup(mods)
     for m in mods:
@@ -165,6 +166,15 @@ class B200KernelMixin:
         self.pack_dtype_bits = 32
         self.pack_factor = 32 // bits
         self.maxq = (1 << bits) - 1
+        # checkpoint layout (2 / 3-bit continuous, planar 3 / 5 / 6 / 7-bit: qlinear/__init__.py:766-773) vs the container
+        # the kernels stream: post_init() widens b-bit codes exactly into 4- or 8-bit fields (layouts.py)
+        if not hasattr(self, "format") or getattr(self, "format", None) is None:
+            self.format = kwargs.get("format")
+        self.planar = layouts.is_planar(bits, self.format)
+        self.kbits = layouts.container_bits(bits)
+        self._kK = in_features         # reduction length / group size the kernels see: differ from in_features /
+        self._kgs = self.group_size    # group_size only after regrouping an arbitrary g_idx (post_init)
+        self._gather: Optional[torch.Tensor] = None
         if not hasattr(self, "name") or self.name is None:
             self.name = kwargs.get("name") or f"{self.__class__.__module__}.{self.__class__.__qualname__}"
         if not hasattr(self, "backend"):
@@ -208,8 +218,10 @@ class B200KernelMixin:
     def convert_gptq_v1_to_v2(self):
         """In-place v1 -> v2 zero-points (what utils/model.py:810-818 does when REQUIRES_FORMAT_V2)."""
         if self._qzeros_format == 1:
-            off = {4: 0x11111111, 8: 0x01010101}[self.bits]
-            self.qzeros.data += off
+            if self.bits in (4, 8) and not self.planar:
+                self.qzeros.data += {4: 0x11111111, 8: 0x01010101}[self.bits]
+            else:  # fields that wrap or straddle words: shift the decoded zero-points (utils/model_dequant.py:900-907)
+                self.qzeros.data.copy_(layouts.shift_zero_points(self.qzeros.data, self.bits, self.planar, +1))
             self._qzeros_format = 2
 
     @torch.no_grad()
@@ -225,7 +237,7 @@ class B200KernelMixin:
         w = linear.weight.data
         if g_idx is None:
             g_idx = torch.arange(self.in_features, dtype=torch.int32, device=w.device) // self.group_size
-        out = pack_gptq(w, scales, zeros, g_idx, self.bits, bias=getattr(linear, "bias", None))
+        out = pack_gptq(w, scales, zeros, g_idx, self.bits, bias=getattr(linear, "bias", None), planar=self.planar)
         mk = lambda t: None if t is None else nn.Parameter(t, requires_grad=False)  # noqa: E731
         self.qweight, self.qzeros, self.scales, self.g_idx = (mk(out[k]) for k in ("qweight", "qzeros", "scales", "g_idx"))
         self.bias = mk(out["bias"])
@@ -258,29 +270,47 @@ class B200KernelMixin:
             raise B2QError("B200QuantLinear needs v2 qzeros; call convert_gptq_v1_to_v2() after loading a v1 file")
         K, N = self.in_features, self.out_features
         gs = self.group_size
+        kb = self.kbits
         with torch.cuda.device(dev):
-            # act-order: sort rows by group so every group is contiguous; x is gathered with the same permutation
-            g_idx = self.g_idx.data.to(torch.int64)
-            trivial = torch.equal(g_idx, torch.arange(K, device=dev) // gs)
-            perm = None
-            if not trivial:
-                counts = torch.bincount(g_idx, minlength=K // gs)
-                if counts.numel() != K // gs or not bool((counts == gs).all()):
-                    raise NotImplementedError(
-                        "B200QuantLinear: g_idx must assign exactly group_size rows to every group")
-                perm = torch.argsort(g_idx, stable=True).to(torch.int32).contiguous()
-            # symmetric layers (every zero-point == 2^(bits-1)) never read qzeros
-            zsym = {4: 0x88888888 - (1 << 32), 8: 0x80808080 - (1 << 32)}[self.bits]
-            is_sym = bool((self.qzeros.data == zsym).all())
-            packed = torch.empty(lib.b2q_packed_bytes(K, N, self.bits), dtype=torch.uint8, device=dev)
             qw = self.qweight.data.contiguous()
+            qz = self.qzeros.data.contiguous()
+            G = qz.shape[0]
+            g_idx = self.g_idx.data.to(torch.int64)
+            trivial = G == K // gs and torch.equal(g_idx, torch.arange(K, device=dev) // gs)
+            uniform = trivial
+            if not trivial and G == K // gs:
+                counts = torch.bincount(g_idx, minlength=G)
+                uniform = counts.numel() == G and bool((counts == gs).all())
+            perm = None
+            if uniform:
+                # act-order: sort rows by group so every group is contiguous; x is gathered with the same permutation
+                if not trivial:
+                    perm = torch.argsort(g_idx, stable=True).to(torch.int32).contiguous()
+                if kb != self.bits or self.planar:
+                    qw, qz, _ = layouts.widen(qw, qz, self.bits, self.planar)
+                kK, kgs = K, gs
+            else:
+                # arbitrary g_idx (unequal groups; a K-slice of an act-order layer with replicated scale tables): sort,
+                # pad every group to a granule with zero-weight rows, re-index the tables per granule (layouts.regroup).
+                # The activations' columns are gathered (and padded) by forward(); the kernels see a plain layer.
+                r = layouts.regroup(layouts.unpack_rows(qw, self.bits, self.planar),
+                                    layouts.unpack_cols(qz, self.bits, self.planar), self.scales.data, g_idx)
+                qw, qz = layouts.pack_rows(r["q"], kb), layouts.pack_cols(r["z"], kb)
+                self.scales.data = r["scales"]
+                self._gather = r["gather"]
+                kK, kgs = int(r["gather"].numel()), int(r["granule"])
+            # symmetric layers (every zero-point == 2^(kbits-1)) never read qzeros
+            zsym = {4: 0x88888888 - (1 << 32), 8: 0x80808080 - (1 << 32)}[kb]
+            is_sym = bool((qz == zsym).all())
+            packed = torch.empty(lib.b2q_packed_bytes(kK, N, kb), dtype=torch.uint8, device=dev)
             # (no stream synchronisation: the repack runs on the current stream and the caching allocator is stream-ordered,
             #  so releasing the checkpoint-layout weights below is safe — 224 syncs per model load otherwise)
-            check(lib.b2q_prepack(_ptr(qw), _ptr(perm), _ptr(packed), K, N, self.bits,
+            check(lib.b2q_prepack(_ptr(qw), _ptr(perm), _ptr(packed), kK, N, kb,
                                   torch.cuda.current_stream(dev).cuda_stream), "b2q_prepack")
+        self._kK, self._kgs = kK, kgs
         self.packed = packed
         self.perm = perm
-        self._zeros_dev = None if is_sym else self.qzeros.data.contiguous()
+        self._zeros_dev = None if is_sym else qz.contiguous()
         self._is_sym = is_sym
         # the checkpoint-layout weights are no longer needed (Marlin/Swordfish free them as well)
         self.qweight = nn.Parameter(torch.empty(0, dtype=torch.int32, device=dev), requires_grad=False)
@@ -338,17 +368,20 @@ class B200KernelMixin:
         out = torch.empty((M, N), dtype=x.dtype, device=x.device)
         if M == 0:
             return out.reshape(out_shape)
+        if self._gather is not None:
+            x2 = x2.index_select(1, self._gather)  # regrouped layer: columns in sorted-by-group order, padded per group
+        kK = self._kK
         ws, ws_bytes = None, 0
         if self.perm is not None:
             # act-order: the tensor-core tiers read x[:, perm] from a workspace (the decode / GEMV tiers gather it while
             # staging the activations and need none; b2q_mm_workspace_bytes mirrors b2q_mm's dispatch exactly)
-            ws_bytes = lib.b2q_mm_workspace_bytes(M, K, N, self.bits, self.group_size, 1)
+            ws_bytes = lib.b2q_mm_workspace_bytes(M, kK, N, self.kbits, self._kgs, 1)
             if ws_bytes:
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         check(
             lib.b2q_mm(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)), _ptr(self._zeros_dev),
-                       _ptr(self.perm), _ptr(self._bias_for(x.dtype)), _ptr(out), M, K, N, self.bits,
-                       self.group_size, _DTYPE_CODE[x.dtype], _ptr(ws), ws_bytes,
+                       _ptr(self.perm), _ptr(self._bias_for(x.dtype)), _ptr(out), M, kK, N, self.kbits,
+                       self._kgs, _DTYPE_CODE[x.dtype], _ptr(ws), ws_bytes,
                        torch.cuda.current_stream(x.device).cuda_stream),
             "b2q_mm",
         )
@@ -369,7 +402,8 @@ class B200KernelMixin:
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         M = x2.shape[0]
-        if not (1 <= M <= DECODE_MAX_M) or self.bits != 4 or self.perm is not None or x.dtype not in _DTYPE_CODE:
+        if not (1 <= M <= DECODE_MAX_M) or self.kbits != 4 or self.perm is not None or self._gather is not None \
+                or x.dtype not in _DTYPE_CODE:
             raise B2QError("forward_allreduce: decode tier only (bits=4, 1 <= tokens <= 8, no act-order, fp16/bf16)")
         if self.adapter:
             # the adapter's low-rank update belongs to the FULL layer output; applying it to one rank's partial sum (or
@@ -379,7 +413,7 @@ class B200KernelMixin:
         check(
             lib.b2q_decode_allreduce(_ptr(x2), _ptr(self.packed), _ptr(self._scales_for(x.dtype)),
                                      _ptr(self._zeros_dev), _ptr(self._bias_for(x.dtype)), _ptr(out), M, K, N,
-                                     self.bits, self.group_size, _DTYPE_CODE[x.dtype], ar.rank, ar.world, ar._peers,
+                                     self.kbits, self._kgs, _DTYPE_CODE[x.dtype], ar.rank, ar.world, ar._peers,
                                      ar.flag_offset, ar.max_elems, ar.ctl.data_ptr(),
                                      torch.cuda.current_stream(x.device).cuda_stream),
             "b2q_decode_allreduce",
@@ -389,12 +423,12 @@ class B200KernelMixin:
     # ---- helpers for tests / tools -------------------------------------------------------------------
     @classmethod
     def from_checkpoint_tensors(cls, qweight, qzeros, scales, g_idx, bits, group_size, bias=None, desc_act=None,
-                                sym=None, device="cuda", dtype=None):
-        """Build + post_init a module from checkpoint-layout tensors (v2 qzeros)."""
+                                sym=None, device="cuda", dtype=None, format=None):
+        """Build + post_init a module from checkpoint-layout tensors (v2 qzeros; `format="gptq_p"` for planar 3-bit)."""
         K = g_idx.shape[0]
         N = qweight.shape[1]
         m = cls(bits=bits, group_size=group_size, desc_act=bool(desc_act), sym=bool(sym) if sym is not None else True,
-                in_features=K, out_features=N, bias=bias is not None, register_buffers=False, dtype=dtype)
+                in_features=K, out_features=N, bias=bias is not None, register_buffers=False, dtype=dtype, format=format)
         mk = lambda t: nn.Parameter(t.detach().clone().contiguous().to(device), requires_grad=False)  # noqa: E731
         m.qweight, m.qzeros, m.scales, m.g_idx = mk(qweight), mk(qzeros), mk(scales), mk(g_idx.to(torch.int32))
         m.bias = mk(bias) if bias is not None else None
@@ -421,13 +455,15 @@ class B200KernelMixin:
                 k0, rows = max(0, K - 256), min(256, K)
             x = torch.zeros((rows, K), dtype=dt, device=dev)
             x[torch.arange(rows, device=dev), torch.arange(k0, k0 + rows, device=dev)] = 1
+            if self._gather is not None:
+                x = x.index_select(1, self._gather)
             ws, ws_bytes = None, 0
             if self.perm is not None:
-                ws_bytes = lib.b2q_workspace_bytes(rows, K, N, 1)
+                ws_bytes = lib.b2q_workspace_bytes(rows, self._kK, N, 1)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             y = out[k0:k0 + rows]
             check(lib.b2q_gemm(_ptr(x), _ptr(self.packed), _ptr(self._scales_for(dt)), _ptr(self._zeros_dev),
-                               _ptr(self.perm), None, _ptr(y), rows, K, N, self.bits, self.group_size, _DTYPE_CODE[dt],
+                               _ptr(self.perm), None, _ptr(y), rows, self._kK, N, self.kbits, self._kgs, _DTYPE_CODE[dt],
                                _ptr(ws), ws_bytes, stream), "b2q_gemm(dequantize_weight)")
         return out
 
@@ -442,8 +478,8 @@ class B200QuantLinear(B200KernelMixin, nn.Module):
     # ---- capability declaration (names follow the reference's BaseQuantLinear) ----
     SUPPORTS_BACKENDS = ["b200"]
     SUPPORTS_METHODS = ["gptq"]
-    SUPPORTS_FORMATS = {"gptq": 120, "gptq_v2": 120}  # > TorchAten 110 (CPU) / Swordfish 101 / Machete 100 / Marlin 90
-    SUPPORTS_BITS = [4, 8]
+    SUPPORTS_FORMATS = {"gptq": 120, "gptq_v2": 120, "gptq_p": 120}  # > TorchAten 110 (CPU) / Swordfish 101 / Machete 100 / Marlin 90
+    SUPPORTS_BITS = [2, 3, 4, 5, 6, 7, 8]  # 4 / 8 native; 2 / 3 widened to 4-bit, 5 / 6 / 7 (planar) to 8-bit fields at post_init
     SUPPORTS_GROUP_SIZE = [-1, 32, 64, 128]
     SUPPORTS_DESC_ACT = [True, False]
     SUPPORTS_SYM = [True, False]

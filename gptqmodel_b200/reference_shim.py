@@ -39,7 +39,7 @@ def make_reference_kernel(base_cls, *, backend, methods, formats, adapters, devi
         SUPPORTS_BACKENDS = [backend]
         SUPPORTS_METHODS = list(methods)
         SUPPORTS_FORMATS = dict(formats)   # > Swordfish 101 / Machete 100 / Marlin 90 wins auto-selection on CUDA
-        SUPPORTS_BITS = [4, 8]
+        SUPPORTS_BITS = [2, 3, 4, 5, 6, 7, 8]  # 2 / 3 and planar 5 / 6 / 7 are widened exactly to 4 / 8-bit fields (layouts.py)
         SUPPORTS_GROUP_SIZE = [-1, 32, 64, 128]
         SUPPORTS_DESC_ACT = [True, False]
         SUPPORTS_SYM = [True, False]
@@ -67,7 +67,7 @@ def make_reference_kernel(base_cls, *, backend, methods, formats, adapters, devi
                               adapter=adapter, register_buffers=False, **kwargs)
             self._b200_setup(bits, group_size, desc_act, sym, in_features, out_features, bias=bias,
                              pack_dtype=pack_dtype, adapter=adapter, register_buffers=register_buffers,
-                             name=kwargs.get("name"), dtype=kwargs.get("dtype"))
+                             name=kwargs.get("name"), dtype=kwargs.get("dtype"), format=kwargs.get("format"))
 
         @classmethod
         def validate_once(cls) -> Tuple[bool, Optional[Exception]]:

@@ -49,11 +49,25 @@ def shard_columns(layer: Layer, rank: int, world: int) -> Layer:
     return out
 
 
+def _row_words(k: int, bits: int, planar: bool) -> int:
+    """First qweight word row of input feature k (k must start a packing block: 32/bits codes, or 32 for the 3-bit
+    stream and the planar layouts)."""
+    blk = 32 if (planar or 32 % bits) else 32 // bits
+    if k % blk != 0:
+        raise NotImplementedError(f"row shard: boundary {k} is not a multiple of the {bits}-bit packing block ({blk})")
+    return k * bits // 32
+
+
 def shard_rows(layer: Layer, rank: int, world: int) -> Layer:
-    """Row-parallel shard: slice the K axis.  Needs K/P to be whole groups and a group-contiguous g_idx."""
+    """Row-parallel shard: slice the K axis (input rows [rank*K/P, (rank+1)*K/P) in CHECKPOINT order).
+
+    Group-contiguous g_idx: K/P must be whole groups; the shard keeps its own rows of the scale / zero tables.
+    Act-order g_idx: the shard's rows belong to arbitrary groups, so it keeps the FULL tables (the reference's rule for its
+    engines: `marlin_repeat_scales_on_all_ranks`, utils/marlin.py:300-305) and its slice of g_idx still indexes them;
+    `B200QuantLinear.post_init` serves such a layer through `layouts.regroup` (out["replicated_tables"] = True)."""
     _check(layer)
     bits = int(layer["bits"])
-    pf = 32 // bits
+    planar = bool(layer.get("planar", False))
     qweight, qzeros, scales, g_idx = layer["qweight"], layer["qzeros"], layer["scales"], layer["g_idx"]
     K = g_idx.shape[0]
     gs = int(layer["group_size"])
@@ -61,26 +75,26 @@ def shard_rows(layer: Layer, rank: int, world: int) -> Layer:
     if K % world != 0:
         raise NotImplementedError(f"row shard: K={K} not divisible by {world}")
     k0, k1 = rank * K // world, (rank + 1) * K // world
-    if int(layer["group_size"]) <= 0 and world > 1:
+    out = dict(layer)
+    out["qweight"] = qweight[_row_words(k0, bits, planar):_row_words(k1, bits, planar)].contiguous()
+    trivial = torch.equal(g_idx.to(torch.int64).cpu(), torch.arange(K) // gs)
+    if not trivial:
+        out["scales"] = scales.contiguous()
+        out["qzeros"] = qzeros.contiguous()
+        out["g_idx"] = g_idx[k0:k1].to(torch.int32).contiguous()
+        out["replicated_tables"] = True
+    elif int(layer["group_size"]) <= 0:
         # one group spans all of K: every rank keeps the single scale row
-        g0, g1 = 0, 1
+        out["scales"] = scales[0:1].contiguous()
+        out["qzeros"] = qzeros[0:1].contiguous()
+        out["g_idx"] = torch.zeros(k1 - k0, dtype=torch.int32, device=g_idx.device)
+        out["group_size"] = -1
     else:
         if (k1 - k0) % gs != 0:
             raise NotImplementedError(f"row shard: K/P={k1 - k0} must be a multiple of group_size={gs}")
         g0, g1 = k0 // gs, k1 // gs
-    trivial = torch.equal(g_idx.to(torch.int64).cpu(), torch.arange(K) // gs)
-    if not trivial:
-        raise NotImplementedError(
-            "row-parallel shard of an act-order layer: scales would have to be replicated and groups are no longer "
-            "whole inside a shard (marlin_repeat_scales_on_all_ranks); not supported by the B2Q tile layout yet")
-    out = dict(layer)
-    out["qweight"] = qweight[k0 // pf:k1 // pf].contiguous()
-    out["scales"] = scales[g0:g1].contiguous()
-    out["qzeros"] = qzeros[g0:g1].contiguous()
-    if int(layer["group_size"]) <= 0:
-        out["g_idx"] = torch.zeros(k1 - k0, dtype=torch.int32, device=g_idx.device)
-        out["group_size"] = -1
-    else:
+        out["scales"] = scales[g0:g1].contiguous()
+        out["qzeros"] = qzeros[g0:g1].contiguous()
         out["g_idx"] = (g_idx[k0:k1] - g0).to(torch.int32).contiguous()
     if layer.get("bias") is not None:
         out["bias"] = layer["bias"] if rank == 0 else None  # added once, before the reduce
@@ -210,12 +224,12 @@ class FusedDecodeAllReduce:
         self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
         self._peers = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
         self.ctl = torch.zeros(4, dtype=torch.int32, device=device)  # {sequence, arrivals, status, -}
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's buffer is zeroed before anybody pushes into it
 
     def status(self) -> int:
         """0, or 1 + the rank of a peer whose flag never arrived within the kernel's 2 s bound (host sync; debugging)."""
         return int(self.ctl[2].item())
-        torch.cuda.synchronize(device)
-        dist.barrier(group)  # every rank's buffer is zeroed before anybody pushes into it
 
 
 class RowParallelLinear(torch.nn.Module):

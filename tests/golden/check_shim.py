@@ -29,7 +29,7 @@ out = {}
 # a maintainer adds BACKEND.GPTQ_B200; any existing member serves the purpose of the check
 backend = getattr(BACKEND, "GPTQ_B200", None) or BACKEND.GPTQ_MARLIN
 B200Linear = make_reference_kernel(GPTQQuantLinear, backend=backend, methods=[METHOD.GPTQ],
-                                   formats={FORMAT.GPTQ: 120, FORMAT.GPTQ_V2: 120}, adapters=[Lora],
+                                   formats={FORMAT.GPTQ: 120, FORMAT.GPTQ_V2: 120, FORMAT.GPTQ_P: 120}, adapters=[Lora],
                                    devices=[DEVICE.CUDA], platforms=[PLATFORM.LINUX])
 out["mro"] = [c.__name__ for c in B200Linear.__mro__][:6]
 B200Linear.verify_supports_params()
@@ -76,11 +76,19 @@ out["name"] = m.name
 out["n_list_buffers"] = len(m.list_buffers())
 bad = None
 try:
-    B200Linear(bits=3, group_size=128, desc_act=False, sym=True, in_features=256, out_features=128,
+    B200Linear(bits=16, group_size=128, desc_act=False, sym=True, in_features=256, out_features=128,
                pack_dtype=torch.int32, bias=False, backend=backend, adapter=None)
 except NotImplementedError:
     bad = "NotImplementedError"
 except Exception as e:  # noqa: BLE001
     bad = type(e).__name__
-out["bits3"] = bad
+out["bits16"] = bad
+# 3-bit continuous and planar 5-bit (format gptq_p) modules: checkpoint-shaped buffers, 4- / 8-bit kernel container
+m3 = B200Linear(bits=3, group_size=128, desc_act=False, sym=True, in_features=256, out_features=128,
+                pack_dtype=torch.int32, bias=False, backend=backend, adapter=None, register_buffers=True)
+m5 = B200Linear(bits=5, group_size=64, desc_act=False, sym=False, in_features=256, out_features=128,
+                pack_dtype=torch.int32, bias=False, backend=backend, adapter=None, register_buffers=True,
+                format=FORMAT.GPTQ_P)
+out["bits3"] = dict(qweight=list(m3.qweight.shape), qzeros=list(m3.qzeros.shape), kbits=m3.kbits, planar=bool(m3.planar))
+out["bits5"] = dict(qweight=list(m5.qweight.shape), qzeros=list(m5.qzeros.shape), kbits=m5.kbits, planar=bool(m5.planar))
 print("SHIM_JSON " + json.dumps(out))

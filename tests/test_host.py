@@ -53,8 +53,11 @@ def test_abi_argument_validation_without_gpu():
 
 
 def test_validate_follows_reference_convention():
-    ok, err = B200QuantLinear.validate(bits=3, group_size=128, in_features=128, out_features=128)
+    ok, err = B200QuantLinear.validate(bits=1, group_size=128, in_features=128, out_features=128)
     assert not ok and isinstance(err, NotImplementedError)
+    for b in (2, 3, 5, 6, 7):  # widened exactly to 4- / 8-bit fields at post_init (gptqmodel_b200/layouts.py)
+        ok, err = B200QuantLinear.validate(bits=b, group_size=128, in_features=128, out_features=128)
+        assert ok and err is None
     ok, err = B200QuantLinear.validate(bits=4, group_size=16, in_features=128, out_features=128)
     assert not ok and isinstance(err, NotImplementedError)
     ok, err = B200QuantLinear.validate(bits=4, group_size=128, in_features=100, out_features=128)
@@ -63,7 +66,7 @@ def test_validate_follows_reference_convention():
                                        pack_dtype=torch.int32, dtype=torch.bfloat16)
     assert ok and err is None
     with pytest.raises(NotImplementedError):
-        B200QuantLinear(bits=2, group_size=128, desc_act=False, sym=True, in_features=128, out_features=128)
+        B200QuantLinear(bits=16, group_size=128, desc_act=False, sym=True, in_features=128, out_features=128)
     for attr in ("SUPPORTS_BACKENDS", "SUPPORTS_METHODS", "SUPPORTS_FORMATS", "SUPPORTS_BITS", "SUPPORTS_GROUP_SIZE",
                  "SUPPORTS_DESC_ACT", "SUPPORTS_SYM", "SUPPORTS_SHARDS", "SUPPORTS_TRAINING", "SUPPORTS_AUTO_PADDING",
                  "SUPPORTS_IN_FEATURES_DIVISIBLE_BY", "SUPPORTS_OUT_FEATURES_DIVISIBLE_BY", "SUPPORTS_PACK_DTYPES",

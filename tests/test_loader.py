@@ -142,3 +142,29 @@ def test_load_awq_checkpoint(tmp_path):
     assert torch.equal(m.qweight.data, t["qweight"])        # AWQ layout until post_init() converts on the device
     with pytest.raises(FileNotFoundError):
         loader.read_quant_config(str(tmp_path / "missing"))
+
+
+def test_load_lowbit_and_planar_checkpoints(tmp_path):
+    """3-bit v1 file (zero-points straddle words: shifted in logical space, utils/model_dequant.py:900-907) and a planar
+    5-bit gptq_p file (v2 zero-points on disk, quantization/config.py:112-114) built from reference-packed tensors."""
+    import numpy as np
+    from gptqmodel_b200 import layouts
+
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "lowbit_cases.npz"))
+    t = lambda n, k: torch.from_numpy(d[f"{n}.{k}"])  # noqa: E731
+    v2 = {k: t("w3_g128_sym", k) for k in ("qweight", "qzeros", "scales", "g_idx")}
+    v1 = dict(v2, qzeros=layouts.shift_zero_points(v2["qzeros"], 3, False, -1))
+    assert not torch.equal(v1["qzeros"], v2["qzeros"])
+    p3 = tmp_path / "w3"
+    p3.mkdir()
+    _write(str(p3), {"m.o_proj": v1}, {"bits": 3, "group_size": 128, "sym": True})
+    m = loader.load_quantized_linears(str(p3), device="cpu")["m.o_proj"]
+    assert m.bits == 3 and m.kbits == 4 and not m.planar and m.qzero_format() == 2
+    assert torch.equal(m.qzeros.data, v2["qzeros"]) and m.qweight.shape == (256 * 3 // 32, 64)
+    p5 = tmp_path / "w5"
+    p5.mkdir()
+    c5 = {k: t("w5_g64_asym", k) for k in ("qweight", "qzeros", "scales", "g_idx", "bias")}
+    _write(str(p5), {"m.o_proj": c5}, {"bits": 5, "group_size": 64, "sym": False, "checkpoint_format": "gptq_p"})
+    m = loader.load_quantized_linears(str(p5), device="cpu")["m.o_proj"]
+    assert m.bits == 5 and m.kbits == 8 and m.planar and torch.equal(m.qzeros.data, c5["qzeros"])
+    assert m.in_features == 128 and m.out_features == 64 and m.bias is not None

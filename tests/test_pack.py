@@ -43,7 +43,7 @@ def test_pack_gptq_matches_oracle_on_random_grids_and_rejects_bad_input():
         b = oracle.pack(W, sc, ze, g_idx, bits)
         assert torch.equal(a["qweight"], b[0]) and torch.equal(a["qzeros"], b[1]) and torch.equal(a["scales"], b[2])
     with pytest.raises(NotImplementedError):
-        pack_gptq(W, sc, ze, g_idx, 3)
+        pack_gptq(W, sc, ze, g_idx, 9)
     with pytest.raises(ValueError):
         pack_gptq(W, sc[:-1], ze, g_idx, 4)
 

@@ -182,7 +182,7 @@ def test_shim_constructs_on_the_reference_signature_and_is_discovered():
 def test_shim_reports_unsupported_configs_as_not_implemented():
     cls = _make()
     cls.validate_once = classmethod(lambda c: (True, None))
-    for bad in (dict(bits=3), dict(group_size=48), dict(in_features=100), dict(out_features=40),
+    for bad in (dict(bits=16), dict(group_size=48), dict(in_features=100), dict(out_features=40),
                 dict(pack_dtype=torch.int16)):
         kw = dict(bits=4, group_size=128, desc_act=False, sym=True, in_features=256, out_features=128,
                   pack_dtype=torch.int32, bias=False, backend="gptq_b200", adapter=None)
@@ -220,5 +220,7 @@ def test_shim_against_the_unmodified_reference_classes():
     assert out["top_for_gptq"] == "B200Linear"
     assert out["validate_without_gpu"] == [False, "NotImplementedError"]
     assert out["shapes"] == {"qweight": [32, 128], "qzeros": [2, 16], "scales": [2, 128], "g_idx": [256], "bias": [128]}
-    assert out["qzeros_format_initial"] == 1 and out["bits3"] == "NotImplementedError"
+    assert out["qzeros_format_initial"] == 1 and out["bits16"] == "NotImplementedError"
+    assert out["bits3"] == dict(qweight=[24, 128], qzeros=[2, 12], kbits=4, planar=False)
+    assert out["bits5"] == dict(qweight=[40, 128], qzeros=[4, 20], kbits=8, planar=True)
     assert out["state_dict_keys"] == ["bias", "g_idx", "qweight", "qzeros", "scales"]

@@ -58,15 +58,18 @@ def _worker(rank, world, port, ret):
             outs = [torch.zeros_like(h) for _ in range(world)]
             dist.all_gather(outs, h)
             ok = ok and torch.equal(torch.cat(outs, dim=1), fwd(up, x))
-        # act-order row shards are refused loudly ...
+        # act-order row shards keep the FULL scale / zero tables and their slice of g_idx (utils/marlin.py:300-305) ...
         ao = make_layer(256, 128, group_size=64, desc_act=True, seed=3)
-        try:
-            tp.shard_rows(ao, rank, world)
-            ok = False
-        except NotImplementedError:
-            pass
-        # ... and served column-parallel between two all-gathers instead (same interface: K/P in, full N out)
         x = (torch.randn(3, 256, generator=torch.Generator().manual_seed(6)) * 0.5).to(torch.float16)
+        rs = tp.shard_rows(ao, rank, world)
+        ok = ok and rs["replicated_tables"] and rs["scales"].shape == ao["scales"].shape
+        ok = ok and torch.equal(rs["g_idx"], ao["g_idx"][rank * 256 // world:(rank + 1) * 256 // world])
+        part = oracle.forward(x[:, rank * 256 // world:(rank + 1) * 256 // world].contiguous(), rs["qweight"], rs["qzeros"],
+                              rs["scales"], rs["g_idx"], rs["bits"], bias=rs["bias"]).float()
+        tp.all_reduce_sum_(part)
+        full = oracle.forward(x, ao["qweight"], ao["qzeros"], ao["scales"], ao["g_idx"], ao["bits"], bias=ao["bias"])
+        ok = ok and (part - full.float()).abs().max().item() < 2e-2 * full.float().abs().max().item()
+        # ... or are served column-parallel between two all-gathers (same interface: K/P in, full N out)
         cs = tp.shard_columns(ao, rank, world)
 
         class Inner(torch.nn.Module):
