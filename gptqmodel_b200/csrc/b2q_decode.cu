@@ -16,7 +16,8 @@
 //    distributed shared memory (no atomics, no workspace, no output zeroing, deterministic);
 //  * every lane issues its 4 x LDG.128 of weights (+ scales) BEFORE griddepcontrol.wait (programmatic dependent
 //    launch): weights never depend on the previous kernel, so consecutive layers overlap their HBM streams;
-//  * act-order: rows sorted by group at prepack, the x[perm[k']] gather is fused into the activation staging.
+//  * act-order: rows sorted by group at prepack; the activation staging reads x and the INVERSE permutation coalesced
+//    and scatters into shared memory (stage_x_act_order, b2q_decode.cuh).
 // Replaces the decode tiers of swordfish_mm (swordfish_mm.cu:216-286, mma.sync + cp.async + atomics) and Marlin's
 // small-M path (marlin_template.h) in the reference.
 #include "b2q_common.cuh"
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     fetch_scales(cur);
   }
 
+  if (PERM) prefetch_inverse_perm(perm + K, K);
   // PDL: let the next kernel start its own weight prefetch; wait for the producer of x only now.
   stamp(1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -151,7 +153,11 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   // A thread's loads (up to SX_UNROLL x 16 bytes, K = 14336 needs 3.5 per thread) are all issued BEFORE the first is
   // consumed: the rolled loop paid one dependent L2 round trip per iteration (2.6 us of the 11 us down_proj launch,
   // profiles/r02_decode_notes.md).
-  {
+  if (PERM) {
+    stage_x_act_order<T>(x, perm + K, sx, xsum, M, K, q0 * 128, (q1 - q0) * 128, kspan);
+    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
+      if ((i & 7) >= M) xsum[i] = 0.f;
+  } else {
     const int n8 = (q1 - q0) * 16;   // uint4 (8 halves) per token row in this CTA's k-range
     const int tot = M * n8;
     const int totr = (tot + 31) & ~31;
@@ -174,17 +180,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
           mm[u] = m;
           jj[u] = j;
           const T* xr = x + (size_t)m * K;
-          if (PERM) {
-            const int4* pp = reinterpret_cast<const int4*>(perm + (size_t)q0 * 128) + 2 * j;
-            const int4 p0 = pp[0], p1 = pp[1];
-            const uint16_t* xu = reinterpret_cast<const uint16_t*>(xr);
-            xv[u].x = (uint32_t)xu[p0.x] | ((uint32_t)xu[p0.y] << 16);
-            xv[u].y = (uint32_t)xu[p0.z] | ((uint32_t)xu[p0.w] << 16);
-            xv[u].z = (uint32_t)xu[p1.x] | ((uint32_t)xu[p1.y] << 16);
-            xv[u].w = (uint32_t)xu[p1.z] | ((uint32_t)xu[p1.w] << 16);
-          } else {
-            xv[u] = reinterpret_cast<const uint4*>(xr + (size_t)q0 * 128)[j];
-          }
+          xv[u] = reinterpret_cast<const uint4*>(xr + (size_t)q0 * 128)[j];
         }
       }
 #pragma unroll

@@ -63,6 +63,87 @@ __device__ __forceinline__ void issue_quad(uint32_t dst, uint32_t bar, const uin
 // warp's bulk-copy ring runs ahead across tile boundaries.
 // Up to DEC_MAX_SETS weight sets that consume the SAME activations (q/k/v, gate/up: "sibling" QuantLinears) are served
 // by one launch: the 32-feature tiles of all sets form one index space (tile_end = running totals).
+// ---- act-order activation staging -------------------------------------------------------------------------------------
+// `perm` (ABI v3) is int32 [2K]: perm[0:K] the sorted-by-group order (x'[k'] = x[perm[k']]), perm[K:2K] its inverse.
+// Round 2 gathered x[perm[k']] with one 2-byte global load per element: 4096 .. 14336 uncoalesced requests per CTA and
+// token, ~2 .. 7 us of LSU time per launch (act-order decode 620 vs 802 tok/s, profiles/r02_bench_n1.json).  Here every
+// CTA reads x and the INVERSE permutation with coalesced 16-byte loads and scatters the halves into the shared staging
+// buffer (sx[m][inv[k] - k0] = x[m][k] for the sorted positions this CTA owns): 8x fewer global requests, the scattered
+// accesses hit shared memory banks instead.  The per-(64-k block, token) sums are taken from shared memory afterwards.
+__device__ __forceinline__ void prefetch_inverse_perm(const int32_t* __restrict__ inv, int K) {
+  // static data: requested into L2 BEFORE griddepcontrol.wait (a layer's 16 .. 56 KB are HBM-cold on every token)
+  for (int i = threadIdx.x * 32; i < K; i += blockDim.x * 32)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(inv + i));
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_x_act_order(const T* __restrict__ x, const int32_t* __restrict__ inv, T* sx,
+                                                  float* xsum, int M, int K, int k0, int kvalid, int kspan) {
+  using E = ET<T>;
+  constexpr int U = 4;  // independent (x, inverse) loads in flight per thread
+  const int n8 = K >> 3;
+  const int tot = M * n8;
+  for (int i0 = threadIdx.x; i0 < tot; i0 += blockDim.x * U) {
+    uint4 xv[U];
+    int4 p0[U], p1[U];
+    int mm[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      mm[u] = -1;
+      if (i < tot) {
+        const int m = i / n8, j = i - m * n8;
+        mm[u] = m;
+        xv[u] = reinterpret_cast<const uint4*>(x + (size_t)m * K)[j];
+        p0[u] = reinterpret_cast<const int4*>(inv)[2 * j];
+        p1[u] = reinterpret_cast<const int4*>(inv)[2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (mm[u] >= 0) {
+        uint16_t* row = reinterpret_cast<uint16_t*>(sx + (size_t)mm[u] * kspan);
+        auto put = [&](int idx, uint32_t h) {
+          const unsigned d = (unsigned)(idx - k0);
+          if (d < (unsigned)kvalid) row[d] = (uint16_t)h;
+        };
+        put(p0[u].x, xv[u].x & 0xffffu);
+        put(p0[u].y, xv[u].x >> 16);
+        put(p0[u].z, xv[u].y & 0xffffu);
+        put(p0[u].w, xv[u].y >> 16);
+        put(p1[u].x, xv[u].z & 0xffffu);
+        put(p1[u].y, xv[u].z >> 16);
+        put(p1[u].z, xv[u].w & 0xffffu);
+        put(p1[u].w, xv[u].w >> 16);
+      }
+    }
+  }
+  __syncthreads();
+  // xsum[(64-k block) * 8 + token] = sum of the block's 64 staged activations: 8 lanes x one 16-byte shared load each
+  const int nblk = kvalid >> 6;
+  const int units = M * nblk * 8;
+  const int unitsr = (units + 31) & ~31;
+  for (int i = threadIdx.x; i < unitsr; i += blockDim.x) {
+    float sm = 0.f;
+    int b = 0, m = 0;
+    if (i < units) {
+      const int l = i & 7, bm = i >> 3;
+      m = bm / nblk;
+      b = bm - m * nblk;
+      const uint4 v = *reinterpret_cast<const uint4*>(sx + (size_t)m * kspan + b * 64 + l * 8);
+      auto f2 = [](uint32_t w) {
+        const T* h = reinterpret_cast<const T*>(&w);
+        return E::to_f(h[0]) + E::to_f(h[1]);
+      };
+      sm = (f2(v.x) + f2(v.y)) + (f2(v.z) + f2(v.w));
+    }
+    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+    if ((i & 7) == 0 && i < units) xsum[b * 8 + m] = sm;
+  }
+}
+
 constexpr int DEC_MAX_SETS = 3;
 struct DecSets {
   int nsets;

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   // in the part of the kernel that overlaps the previous layer (PDL), so it is free
   __syncthreads();
 
+  if (PERM) prefetch_inverse_perm(perm + K, K);
   stamp(1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -215,8 +216,13 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     }
     if (ngroups > 1) __syncthreads();
     else __syncwarp();
+  } else if (PERM) {
+    stage_x_act_order<T>(x, perm + K, sx, xsum, M, K, q0 * 128, (q1 - q0) * 128, kspan);
+    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
+      if ((i & 7) >= M) xsum[i] = 0.f;
+    __syncthreads();
   } else {
-    // act-order gather (or B2Q_DECODE2_XTMA=0): the staging loop of v1, 4 independent loads in flight per thread
+    // LDG staging (B2Q_DECODE2_XTMA=0, the default): the staging loop of v1
     const int n8 = (q1 - q0) * 16;  // uint4 (8 halves) per token row in this CTA's k-range
     const int tot = M * n8;
     const int totr = (tot + 31) & ~31;
@@ -227,17 +233,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         m = i / n8;
         j = i - m * n8;
         const T* xr = x + (size_t)m * K;
-        if (PERM) {
-          const int4* pp = reinterpret_cast<const int4*>(perm + (size_t)q0 * 128) + 2 * j;
-          const int4 p0 = pp[0], p1 = pp[1];
-          const uint16_t* xu = reinterpret_cast<const uint16_t*>(xr);
-          xv.x = (uint32_t)xu[p0.x] | ((uint32_t)xu[p0.y] << 16);
-          xv.y = (uint32_t)xu[p0.z] | ((uint32_t)xu[p0.w] << 16);
-          xv.z = (uint32_t)xu[p1.x] | ((uint32_t)xu[p1.y] << 16);
-          xv.w = (uint32_t)xu[p1.z] | ((uint32_t)xu[p1.w] << 16);
-        } else {
-          xv = reinterpret_cast<const uint4*>(xr + (size_t)q0 * 128)[j];
-        }
+        xv = reinterpret_cast<const uint4*>(xr + (size_t)q0 * 128)[j];
         reinterpret_cast<uint4*>(sx + (size_t)m * kspan)[j] = xv;
       }
       auto f2 = [](uint32_t u) {

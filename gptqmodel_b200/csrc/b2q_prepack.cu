@@ -85,19 +85,87 @@ int launch_prepack(const void* qweight, const int32_t* perm, void* out, int K, i
   return (int)cudaGetLastError();
 }
 
-// x'[m, k'] = x[m, perm[k']]  (act-order activation gather for the GEMM path; the GEMV fuses it).
+// x'[m, k'] = x[m, perm[k']]  (act-order activation gather for the tensor-core tiers; the decode tiers fuse it).
 // Same job as permute_cols_kernel in the reference's Marlin (gptq_marlin.cu:86-164).
-template <typename T>
-__global__ void permute_cols_kernel(const T* __restrict__ x, const int32_t* __restrict__ perm, T* __restrict__ out,
-                                    int M, int K) {
+// Round 2 issued one 2-byte global load per element (M x K uncoalesced requests: the act-order prefill ran at 922 instead of
+// 1089 TFLOP/s).  Here a CTA stages one row of x in shared memory with coalesced 16-byte loads, gathers from shared memory
+// and writes 16-byte rows; the thread's slice of `perm` is read once and reused for every row the CTA walks.
+template <int UNITS>
+__global__ void __launch_bounds__(256)
+    permute_rows_kernel(const uint16_t* __restrict__ x, const int32_t* __restrict__ perm, uint16_t* __restrict__ out, int M,
+                        int K) {
+  extern __shared__ __align__(16) uint4 srow[];
+  const int n8 = K >> 3;
+  int4 p0[UNITS], p1[UNITS];
+#pragma unroll
+  for (int u = 0; u < UNITS; ++u) {
+    const int j = threadIdx.x + u * 256;
+    if (j < n8) {
+      p0[u] = reinterpret_cast<const int4*>(perm)[2 * j];
+      p1[u] = reinterpret_cast<const int4*>(perm)[2 * j + 1];
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // x is the previous kernel's output; `out` may still be read by it
+  const uint16_t* s = reinterpret_cast<const uint16_t*>(srow);
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
+#pragma unroll
+    for (int u = 0; u < UNITS; ++u) {
+      const int j = threadIdx.x + u * 256;
+      if (j < n8) srow[j] = xr[j];
+    }
+    __syncthreads();
+    uint4* orow = reinterpret_cast<uint4*>(out + (size_t)m * K);
+#pragma unroll
+    for (int u = 0; u < UNITS; ++u) {
+      const int j = threadIdx.x + u * 256;
+      if (j < n8) {
+        uint4 o;
+        o.x = (uint32_t)s[p0[u].x] | ((uint32_t)s[p0[u].y] << 16);
+        o.y = (uint32_t)s[p0[u].z] | ((uint32_t)s[p0[u].w] << 16);
+        o.z = (uint32_t)s[p1[u].x] | ((uint32_t)s[p1[u].y] << 16);
+        o.w = (uint32_t)s[p1[u].z] | ((uint32_t)s[p1[u].w] << 16);
+        orow[j] = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// any K (no shared-memory row): the element-wise form
+__global__ void permute_cols_kernel(const uint16_t* __restrict__ x, const int32_t* __restrict__ perm,
+                                    uint16_t* __restrict__ out, int M, int K) {
   for (int m = blockIdx.y; m < M; m += gridDim.y)
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x)
       out[(size_t)m * K + k] = x[(size_t)m * K + perm[k]];
 }
 
+template <int UNITS>
+static int launch_permute_rows(const void* x, const int32_t* perm, void* out, int M, int K, cudaStream_t stream) {
+  auto kern = permute_rows_kernel<UNITS>;
+  const size_t smem = (size_t)K * 2;  // <= 32 KB: inside the default dynamic shared memory limit
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(M < 148 * 8 ? M : 148 * 8, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env().disable_pdl ? 0 : 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, (const uint16_t*)x, perm, (uint16_t*)out, M, K);
+}
+
 int launch_permute_cols(const void* x, const int32_t* perm, void* out, int M, int K, cudaStream_t stream) {
+  if (K % 8 == 0 && K <= 16384) {
+    if (K <= 4096) return launch_permute_rows<2>(x, perm, out, M, K, stream);
+    if (K <= 8192) return launch_permute_rows<4>(x, perm, out, M, K, stream);
+    return launch_permute_rows<8>(x, perm, out, M, K, stream);
+  }
   dim3 grid((K + 255) / 256 > 64 ? 64 : (K + 255) / 256, M > 32768 ? 32768 : M);
-  permute_cols_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)x, perm, (uint16_t*)out, M, K);
+  permute_cols_kernel<<<grid, 256, 0, stream>>>((const uint16_t*)x, perm, (uint16_t*)out, M, K);
   return (int)cudaGetLastError();
 }
 

@@ -285,7 +285,12 @@ class B200KernelMixin:
             if uniform:
                 # act-order: sort rows by group so every group is contiguous; x is gathered with the same permutation
                 if not trivial:
-                    perm = torch.argsort(g_idx, stable=True).to(torch.int32).contiguous()
+                    # int32 [2K]: the order followed by its inverse (include/b2q.h: the decode tiers scatter through the
+                    # inverse, the tensor-core tiers gather through the order)
+                    order = torch.argsort(g_idx, stable=True)
+                    inv = torch.empty_like(order)
+                    inv[order] = torch.arange(K, device=dev)
+                    perm = torch.cat([order, inv]).to(torch.int32).contiguous()
                 if kb != self.bits or self.planar:
                     qw, qz, _ = layouts.widen(qw, qz, self.bits, self.planar)
                 kK, kgs = K, gs

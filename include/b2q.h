@@ -17,7 +17,9 @@
  *
  * Checkpoint tensors consumed (gptqmodel/nn_modules/qlinear/__init__.py:827-865):
  *   qweight int32 [K*bits/32, N], qzeros int32 [G, N*bits/32] (v2 = true zero-point), scales [G, N],
- *   g_idx int32 [K].  The host derives perm = stable argsort(g_idx) for act-order layers.
+ *   g_idx int32 [K].  The host derives perm = stable argsort(g_idx) for act-order layers and hands the forward entry points
+ *   an int32 [2K] array: perm[0:K] that order (x'[k'] = x[perm[k']]), perm[K:2K] its INVERSE (the decode tiers read x
+ *   coalesced and scatter through the inverse; ABI v3).  b2q_prepack and b2q_permute_cols read perm[0:K] only.
  */
 #ifndef B2Q_H_
 #define B2Q_H_
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B2Q_ABI_VERSION 2
+#define B2Q_ABI_VERSION 3
 #define B2Q_DTYPE_F16 0
 #define B2Q_DTYPE_BF16 1
 
@@ -60,7 +62,7 @@ int b2q_prepack(const int32_t* qweight, const int32_t* perm, void* packed, int K
  * The call runs on the device that owns `packed`, whatever the caller's current device is.
  *   x, scales, bias, out : fp16 (dtype 0) or bf16 (dtype 1), all the same type; x and out contiguous row-major
  *   qzeros               : NULL for symmetric layers (zero-point 2^(bits-1)), else int32 [G, N*bits/32]
- *   perm                 : NULL, or int32 [K] act-order permutation used at prepack
+ *   perm                 : NULL, or int32 [2K]: the act-order permutation used at prepack followed by its inverse
  *   group_size           : 32 | 64 | 128 | K (per-channel; the reference's -1)
  *   workspace            : >= b2q_workspace_bytes(M, K, N, perm != NULL) bytes, may be NULL when that is 0 */
 int b2q_mm(const void* x, const void* packed, const void* scales, const int32_t* qzeros, const int32_t* perm,
@@ -85,7 +87,7 @@ int b2q_gemm(const void* x, const void* packed, const void* scales, const int32_
 /* Sibling layers that consume the SAME activations (q/k/v, gate/up; module order in the reference:
  * gptqmodel/models/definitions/llama.py:17-27) in ONE decode launch: nsets <= 3 weight sets given as HOST arrays of
  * device pointers; all sets share M <= 8, K, bits = 4, group_size, dtype, symmetry (qzeros all NULL or all non-NULL) and
- * the act-order permutation `perm` (NULL, or int32 [K] — q/k/v and gate/up of a GPTQ checkpoint are quantised against the
+ * the act-order permutation `perm` (NULL, or int32 [2K], permutation + inverse — q/k/v and gate/up of a GPTQ checkpoint are quantised against the
  * same input Hessian and therefore carry the same g_idx).  out[i] is [M, N[i]].  Same arithmetic as nsets separate b2q_decode calls; results are bit-identical
  * whenever the fused launch cuts K like the single launches would (see b2q_debug_decode_plan), else they differ only
  * in the order the fp32 partial sums are added. */

@@ -54,7 +54,7 @@ def test_prepack_layout_bit_exact():
         mod = _module(L)
         codes = oracle.unpack_qweight(L["qweight"], bits)  # [K, N]
         if mod.perm is not None:
-            codes = codes[mod.perm.cpu().long()]
+            codes = codes[mod.perm[:256].cpu().long()]  # perm = [order | inverse] (ABI v3)
         K, N = 256, 128
         raw = torch.from_numpy(mod.packed.cpu().numpy().view("uint32").astype("int64"))
         got = torch.zeros(K, N, dtype=torch.int64)
