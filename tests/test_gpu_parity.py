@@ -258,13 +258,18 @@ def test_batched_and_empty_shapes():
     assert_close_rel(mod(xs), oracle_forward(L, xs.cpu()), 1e-3)
 
 
-def test_nonuniform_g_idx_rejected():
+def test_nonuniform_g_idx_is_served():
+    """One row moved to another group (63 / 65 rows instead of 64 / 64): round 1 refused such a layer; it is now regrouped
+    (gptqmodel_b200/layouts.py::regroup) and must match the oracle, which walks g_idx directly like the reference."""
     L = make_layer(256, 128, group_size=64, seed=5)
     gi = L["g_idx"].clone()
     gi[0] = 3  # group 0 loses a row, group 3 gains one
     L["g_idx"] = gi
-    with pytest.raises(NotImplementedError):
-        _module(L)
+    mod = _module(L)
+    assert mod._gather is not None and mod.perm is None
+    for M in (1, 3, 40, 200):
+        x = (torch.randn(M, 256, generator=torch.Generator().manual_seed(M)) * 0.5).to(torch.float16).to(DEV)
+        assert_layer_close(mod(x), L, x, 1e-3, f"non-uniform g_idx M={M}")
 
 
 @pytest.mark.parametrize("K,N", [(4096, 14336), (14336, 4096), (4096, 4096), (4096, 1024)])
