@@ -143,6 +143,11 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   }
 
   if (PERM) prefetch_inverse_perm(perm + K, K);
+  // zero the token columns >= M of the block sums once (read by the fix-up of lanes whose columns are padding): own shared
+  // memory, nothing to wait for — everything between griddepcontrol.wait and the first main-loop iteration is on the critical
+  // path of every launch (profiles/r02_actorder_notes.md)
+  for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
+    if ((i & 7) >= M) xsum[i] = 0.f;
   // PDL: let the next kernel start its own weight prefetch; wait for the producer of x only now.
   stamp(1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -155,8 +160,6 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   // profiles/r02_decode_notes.md).
   if (PERM) {
     stage_x_act_order<T>(x, perm + K, sx, xsum, M, K, q0 * 128, (q1 - q0) * 128, kspan);
-    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
-      if ((i & 7) >= M) xsum[i] = 0.f;
   } else {
     const int n8 = (q1 - q0) * 16;   // uint4 (8 halves) per token row in this CTA's k-range
     const int tot = M * n8;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         mm[u] = 0;
         jj[u] = 0;
         if (i < tot) {
-          const int m = i / n8, j = i - m * n8;
+          const int m = (M == 1) ? 0 : i / n8, j = i - m * n8;  // batch-1 decode: no integer division ahead of the load
           mm[u] = m;
           jj[u] = j;
           const T* xr = x + (size_t)m * K;
@@ -196,9 +199,6 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         }
       }
     }
-    // zero the token columns >= M once (read by the fix-up of lanes whose columns are padding)
-    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
-      if ((i & 7) >= M) xsum[i] = 0.f;
   }
   __syncthreads();
   stamp(3);

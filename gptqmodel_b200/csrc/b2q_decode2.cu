@@ -174,6 +174,11 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   __syncthreads();
 
   if (PERM) prefetch_inverse_perm(perm + K, K);
+  // the block sums' padding columns (tokens >= M) are zeroed before the wait (LDG / act-order staging; the bulk-copy
+  // variant writes every column itself)
+  if (!XTMA)
+    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
+      if ((i & 7) >= M) xsum[i] = 0.f;
   stamp(1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -218,8 +223,6 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     else __syncwarp();
   } else if (PERM) {
     stage_x_act_order<T>(x, perm + K, sx, xsum, M, K, q0 * 128, (q1 - q0) * 128, kspan);
-    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
-      if ((i & 7) >= M) xsum[i] = 0.f;
     __syncthreads();
   } else {
     // LDG staging (B2Q_DECODE2_XTMA=0, the default): the staging loop of v1
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       uint4 xv = make_uint4(0, 0, 0, 0);
       int m = 0, j = 0;
       if (i < tot) {
-        m = i / n8;
+        m = (M == 1) ? 0 : i / n8;  // batch-1 decode: no integer division ahead of the load
         j = i - m * n8;
         const T* xr = x + (size_t)m * K;
         xv = reinterpret_cast<const uint4*>(xr + (size_t)q0 * 128)[j];
@@ -246,8 +249,6 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       sm += __shfl_xor_sync(0xffffffffu, sm, 4);
       if ((i & 7) == 0 && i < tot) xsum[(j >> 3) * 8 + m] = sm;
     }
-    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
-      if ((i & 7) >= M) xsum[i] = 0.f;
     __syncthreads();
   }
   stamp(3);
