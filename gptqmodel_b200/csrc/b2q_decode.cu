@@ -146,8 +146,13 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   // zero the token columns >= M of the block sums once (read by the fix-up of lanes whose columns are padding): own shared
   // memory, nothing to wait for — everything between griddepcontrol.wait and the first main-loop iteration is on the critical
   // path of every launch (profiles/r02_actorder_notes.md)
-  for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
-    if ((i & 7) >= M) xsum[i] = 0.f;
+  const bool OWN = !PERM && ngroups == 1;  // per-warp staging (stage_x_own_quads): no CTA barrier before the main loop
+  if (OWN) {
+    zero_own_xsum_padding(xsum, M, nq, wg, gw);
+  } else {
+    for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
+      if ((i & 7) >= M) xsum[i] = 0.f;
+  }
   // PDL: let the next kernel start its own weight prefetch; wait for the producer of x only now.
   stamp(1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -158,7 +163,9 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   // A thread's loads (up to SX_UNROLL x 16 bytes, K = 14336 needs 3.5 per thread) are all issued BEFORE the first is
   // consumed: the rolled loop paid one dependent L2 round trip per iteration (2.6 us of the 11 us down_proj launch,
   // profiles/r02_decode_notes.md).
-  if (PERM) {
+  if (OWN) {
+    stage_x_own_quads<T>(x, sx, xsum, M, K, q0, nq, wg, gw, kspan);
+  } else if (PERM) {
     stage_x_act_order<T>(x, perm + K, sx, xsum, M, K, q0 * 128, (q1 - q0) * 128, kspan);
   } else {
     const int n8 = (q1 - q0) * 16;   // uint4 (8 halves) per token row in this CTA's k-range
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
       }
     }
   }
-  __syncthreads();
+  if (!OWN) __syncthreads();
   stamp(3);
 
   // ---- 3. loop over this CTA's tiles; inside a tile the warps split the k-quads --------------------

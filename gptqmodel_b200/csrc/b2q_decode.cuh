@@ -144,6 +144,67 @@ __device__ __forceinline__ void stage_x_act_order(const T* __restrict__ x, const
   }
 }
 
+// ---- per-warp activation staging (no act-order, one warp group) ------------------------------------------------------------
+// Warp `wg` of `gw` stages exactly the k-quads it reads in the main loop (quads wg, wg + gw, ... of the CTA's k-range: 16
+// lanes x 16 bytes per quad and token) and their 64-k block sums, so only the WARP synchronises between the load of x and its
+// first mma — the CTA-wide loop it replaces made every warp wait at a CTA barrier for the slowest L2 round trip of the CTA.
+// Everything between griddepcontrol.wait and the first main-loop iteration is on the critical path of every launch
+// (profiles/r02_actorder_notes.md: trimming it moved the whole Llama-3-8B decode step by 5 + 4 %).
+__device__ __forceinline__ void zero_own_xsum_padding(float* xsum, int M, int nq, int wg, int gw) {
+  // token columns >= M of this warp's block sums (read by the fix-up of lanes whose columns are padding); before the wait
+  const int lane = threadIdx.x & 31;
+  for (int idx = lane; idx < nq * 16; idx += 32) {
+    const int qi = idx >> 4, b = (idx >> 3) & 1, m = idx & 7;
+    if (m >= M) xsum[((wg + qi * gw) * 2 + b) * 8 + m] = 0.f;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_x_own_quads(const T* __restrict__ x, T* sx, float* xsum, int M, int K, int q0, int nq,
+                                                  int wg, int gw, int kspan) {
+  using E = ET<T>;
+  constexpr int U = 4;  // independent 16-byte loads in flight per lane
+  const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
+  const int np = (nq + 1) >> 1;  // quad pairs: one warp-wide load covers two quads
+  const int units = M * np;      // (token, quad pair)
+  auto f2 = [](uint32_t w) {
+    const T* h = reinterpret_cast<const T*>(&w);
+    return E::to_f(h[0]) + E::to_f(h[1]);
+  };
+  for (int v0 = 0; v0 < units; v0 += U) {
+    uint4 xv[U];
+    int mm[U], ql[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u;
+      xv[u] = make_uint4(0, 0, 0, 0);
+      mm[u] = 0;
+      ql[u] = -1;
+      if (v < units) {
+        const int m = (M == 1) ? 0 : v / np;  // batch-1 decode: no integer division ahead of the load
+        const int qi = 2 * (v - m * np) + half;
+        if (qi < nq) {
+          mm[u] = m;
+          ql[u] = wg + qi * gw;
+          xv[u] = reinterpret_cast<const uint4*>(x + (size_t)m * K + (size_t)q0 * 128)[ql[u] * 16 + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (v0 + u < units) {  // warp-uniform
+        if (ql[u] >= 0) reinterpret_cast<uint4*>(sx + (size_t)mm[u] * kspan)[ql[u] * 16 + j] = xv[u];
+        float sm = (f2(xv[u].x) + f2(xv[u].y)) + (f2(xv[u].z) + f2(xv[u].w));
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+        if (ql[u] >= 0 && (j & 7) == 0) xsum[(ql[u] * 2 + (j >> 3)) * 8 + mm[u]] = sm;  // 8 lanes = one 64-k block
+      }
+    }
+  }
+  __syncwarp();
+}
+
 constexpr int DEC_MAX_SETS = 3;
 struct DecSets {
   int nsets;

@@ -176,9 +176,13 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   if (PERM) prefetch_inverse_perm(perm + K, K);
   // the block sums' padding columns (tokens >= M) are zeroed before the wait (LDG / act-order staging; the bulk-copy
   // variant writes every column itself)
-  if (!XTMA)
+  const bool OWN = !XTMA && !PERM && ngroups == 1;  // per-warp staging (stage_x_own_quads): no CTA barrier before the loop
+  if (OWN) {
+    zero_own_xsum_padding(xsum, M, nq, wg, gw);
+  } else if (!XTMA) {
     for (int i = threadIdx.x; i < (q1 - q0) * 2 * 8; i += blockDim.x)
       if ((i & 7) >= M) xsum[i] = 0.f;
+  }
   stamp(1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     }
     if (ngroups > 1) __syncthreads();
     else __syncwarp();
+  } else if (OWN) {
+    stage_x_own_quads<T>(x, sx, xsum, M, K, q0, nq, wg, gw, kspan);
   } else if (PERM) {
     stage_x_act_order<T>(x, perm + K, sx, xsum, M, K, q0 * 128, (q1 - q0) * 128, kspan);
     __syncthreads();
