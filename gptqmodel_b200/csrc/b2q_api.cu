@@ -490,4 +490,47 @@ int b2q_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int dt
   return check_cuda(launch_moe_combine(ypair, y, T, top_k, N, dtype, (cudaStream_t)stream), "b2q_moe_combine");
 }
 
+// ---- MoE decode: one token through its top_k experts on the decode tier (b2q_decode.cu, DecSets::moe) ---------------------
+int b2q_moe_decode_gate_up(const void* x, const void* packed1, const void* scales1, const int32_t* qzeros1,
+                           const void* packed3, const void* scales3, const int32_t* qzeros3, const int32_t* topk_ids,
+                           int top_k, int E, int K, int N, int bits, int group_size, int dtype, void* gu, void* stream) {
+  int v = validate("b2q_moe_decode_gate_up", x, packed1, scales1, gu, 1, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (packed3 == nullptr || scales3 == nullptr || topk_ids == nullptr || E < 1 ||
+      (reinterpret_cast<uintptr_t>(packed3) & 15)) {
+    set_error("b2q_moe_decode_gate_up: w3 stack / topk_ids missing or misaligned (E=%d)", E);
+    return -2;
+  }
+  DeviceGuard dg(packed1);
+  MmArgs a = make_args(x, packed1, scales1, qzeros1, nullptr, nullptr, gu, 1, K, N, bits, group_size, dtype, nullptr, 0,
+                       stream);
+  return check_cuda(launch_moe_decode_gate_up(a, packed1, scales1, qzeros1, packed3, scales3, qzeros3, topk_ids, top_k, E,
+                                              gu), "b2q_moe_decode_gate_up");
+}
+
+int b2q_moe_decode_act(const void* gu, void* h, int top_k, int N, int dtype, void* stream) {
+  if (gu == nullptr || h == nullptr || top_k < 1 || N < 2 || N % 2 != 0 || (dtype != 0 && dtype != 1) ||
+      (reinterpret_cast<uintptr_t>(gu) & 3) || (reinterpret_cast<uintptr_t>(h) & 3)) {
+    set_error("b2q_moe_decode_act: bad argument (top_k=%d N=%d)", top_k, N);
+    return -2;
+  }
+  DeviceGuard dg(h);
+  return check_cuda(launch_moe_decode_act(gu, h, top_k, N, dtype, (cudaStream_t)stream), "b2q_moe_decode_act");
+}
+
+int b2q_moe_decode_down(const void* h, const void* packed2, const void* scales2, const int32_t* qzeros2,
+                        const int32_t* topk_ids, const float* topk_weights, int top_k, int E, int K, int N, int bits,
+                        int group_size, int dtype, void* y, void* stream) {
+  int v = validate("b2q_moe_decode_down", h, packed2, scales2, y, 1, K, N, bits, group_size, dtype);
+  if (v != 0) return v;
+  if (topk_ids == nullptr || topk_weights == nullptr || E < 1) {
+    set_error("b2q_moe_decode_down: topk_ids / topk_weights missing (E=%d)", E);
+    return -2;
+  }
+  DeviceGuard dg(packed2);
+  MmArgs a = make_args(h, packed2, scales2, qzeros2, nullptr, nullptr, y, 1, K, N, bits, group_size, dtype, nullptr, 0,
+                       stream);
+  return check_cuda(launch_moe_decode_down(a, topk_ids, topk_weights, top_k, E), "b2q_moe_decode_down");
+}
+
 }  // extern "C"

@@ -26,7 +26,8 @@
 
 namespace b2q {
 
-template <typename T, bool ASYM, bool G64>
+// MOE: a separate instantiation for the one-token MoE launches (DecSets::moe), so that the dense kernels carry none of it
+template <typename T, bool ASYM, bool G64, bool MOE>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     decode_kernel(const __grid_constant__ DecSets S, const int32_t* __restrict__ perm, const T* __restrict__ x, int M,
                   int K, int gsh, int qpc, int max_tiles, int ngroups, int stl,
@@ -42,6 +43,9 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     }
   };
   stamp(0);
+  // MoE decode (DecSets::moe): the experts are data of an earlier kernel, so nothing expert-dependent may be prefetched
+  // ahead of the PDL wait — the wait moves to the top (the later one is then a no-op)
+  if (MOE) asm volatile("griddepcontrol.wait;" ::: "memory");
   // dynamic smem: ring[nwarps][DEC_STAGES][2 KB] | sx[M][kspan] (T) | xsum[kblocks][8] | red[2][nwarps][8][32] |
   //               part[max_tiles][8][32] | mbarriers[nwarps][DEC_STAGES]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -56,9 +60,11 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const int TT = S.tile_end[S.nsets - 1];       // tiles of all sets
   const int ntiles = (tile0 < TT) ? (TT - tile0 + C - 1) / C : 0;  // tiles of this group
   const int nquads = K >> 7;
-  const int q0 = blockIdx.y * qpc;
+  // moe == 2: every cluster rank owns a whole expert (k-range 0 .. K of ITS weights) and its own row of activations
+  const int q0 = (MOE && S.moe == 2) ? 0 : blockIdx.y * qpc;
   const int q1 = min(q0 + qpc, nquads);
   const int kspan = qpc * 128;
+  if (MOE && S.moe == 2) x += (size_t)blockIdx.y * K;
   const int nst = 1 << stl;  // ring stages per warp (2 or 4)
   uint8_t* ring = dsm + (size_t)warp * nst * DEC_QUAD_BYTES;
   T* sx = reinterpret_cast<T*>(dsm + (size_t)nwarps * nst * DEC_QUAD_BYTES);
@@ -77,7 +83,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   size_t iss_kbs = 0;  // k-block stride (uint4) of the set being issued
   int iss_q = 0, iss_u = 0, iss_ti = 0;
   auto iss_begin_tile = [&]() {
-    const TileRef<T> r = resolve_tile<T>(S, tile0 + iss_ti * C);
+    const TileRef<T> r = resolve_tile<T, MOE>(S, tile0 + iss_ti * C);
     iss_kbs = (size_t)(r.N >> 4) * 32;
     iss_src = r.w + (size_t)(2 * (q0 + wg)) * iss_kbs + (size_t)(2 * r.nt) * 32;
   };
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const uint32_t* zq_next = nullptr;
   int pre_q = 0, pre_ti = 0, pre_N = 0;
   auto pre_begin_tile = [&]() {
-    const TileRef<T> r = resolve_tile<T>(S, tile0 + pre_ti * C);
+    const TileRef<T> r = resolve_tile<T, MOE>(S, tile0 + pre_ti * C);
     pre_N = r.N;
     sc_next = r.sc + (size_t)g_first * r.N + r.nt * 32 + g;
     if (ASYM) zq_next = r.zq + (size_t)g_first * (r.N >> 3) + r.nt * 4;
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   if (ar.world > 1) ar_seq = *reinterpret_cast<const volatile uint32_t*>(ar.ctl);
   int u = 0;
   for (int ti = 0; ti < ntiles; ++ti) {
-    const TileRef<T> tr = resolve_tile<T>(S, tile0 + ti * C);
+    const TileRef<T> tr = resolve_tile<T, MOE>(S, tile0 + ti * C);
     const int nt = tr.nt, N = tr.N;
     const T* bias = tr.bias;
     T* out = tr.out;
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     }
     __syncthreads();
     if (ntiles > 0) {
-      const TileRef<T> tr = resolve_tile<T>(S, tile0);
+      const TileRef<T> tr = resolve_tile<T, MOE>(S, tile0);
       const float* mine = reinterpret_cast<const float*>(ar.buf[ar.rank]) + (size_t)(ar_seq & 1u) * ar.world * ar.max_elems;
       for (int i = wg * 32 + lane; i < 256; i += gw * 32) {
         const int acc = i >> 5, ln = i & 31;
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     const uint32_t rank = cluster_ctarank();
     // each group reduces its own tiles (same tile <-> group mapping in every rank of the cluster)
     for (int ti = (int)rank; ti < ntiles; ti += (int)nrank) {
-      const TileRef<T> tr = resolve_tile<T>(S, tile0 + ti * C);
+      const TileRef<T> tr = resolve_tile<T, MOE>(S, tile0 + ti * C);
       const int nt = tr.nt, N = tr.N;
       const T* bias = tr.bias;
       T* out = tr.out;
@@ -403,7 +409,12 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
         const int m = 2 * (ln & 3) + (acc & 1);
         if (m < M) {
           float v = 0.f;
-          for (uint32_t r = 0; r < nrank; ++r) v += ld_dsmem_f32(smem_u32(&part[(grp * max_tiles + ti) * 256 + i]), r);
+          for (uint32_t r = 0; r < nrank; ++r) {
+            float pr = ld_dsmem_f32(smem_u32(&part[(grp * max_tiles + ti) * 256 + i]), r);
+            // MoE down: rank r holds expert r's complete output: y_r = T(h_r W2) like the module, then the routing weight
+            if (MOE && S.moe == 2) pr = S.wts[r] * E::to_f(E::from_f(pr));
+            v += pr;
+          }
           const int n = nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
           T o = E::from_f(v);
           if (bias != nullptr) o = E::from_f(E::to_f(o) + E::to_f(bias[n]));
@@ -485,9 +496,9 @@ bool decode_plan(int version, const MmArgs& a, int NT, int* out8) {
   return true;
 }
 
-template <typename T, bool ASYM, bool G64>
+template <typename T, bool ASYM, bool G64, bool MOE = false>
 static int launch_decode_t(const MmArgs& a, const DecSets& sets, const DecodeCfg& c, const DecodeAR& ar) {
-  auto kern = decode_kernel<T, ASYM, G64>;
+  auto kern = decode_kernel<T, ASYM, G64, MOE>;
   if (c.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return (int)e;
@@ -548,12 +559,13 @@ static int launch_decode_sets(const MmArgs& a, const DecSets& sets) {
   }
   const bool asym = a.qzeros != nullptr, g64 = a.group_size == 64;
   const DecodeAR none = {};
-#define B2Q_DEC_CASE(T)                                                          \
-  (asym ? (g64 ? launch_decode_t<T, true, true>(a, sets, c, none)                \
-               : launch_decode_t<T, true, false>(a, sets, c, none))              \
-        : (g64 ? launch_decode_t<T, false, true>(a, sets, c, none)               \
-               : launch_decode_t<T, false, false>(a, sets, c, none)))
-  return a.dtype == 0 ? B2Q_DEC_CASE(__half) : B2Q_DEC_CASE(__nv_bfloat16);
+#define B2Q_DEC_CASE(T, MOE)                                                     \
+  (asym ? (g64 ? launch_decode_t<T, true, true, MOE>(a, sets, c, none)           \
+               : launch_decode_t<T, true, false, MOE>(a, sets, c, none))         \
+        : (g64 ? launch_decode_t<T, false, true, MOE>(a, sets, c, none)          \
+               : launch_decode_t<T, false, false, MOE>(a, sets, c, none)))
+  if (sets.moe != 0) return a.dtype == 0 ? B2Q_DEC_CASE(__half, true) : B2Q_DEC_CASE(__nv_bfloat16, true);
+  return a.dtype == 0 ? B2Q_DEC_CASE(__half, false) : B2Q_DEC_CASE(__nv_bfloat16, false);
 #undef B2Q_DEC_CASE
 }
 
@@ -626,6 +638,102 @@ int launch_decode_multi(const MmArgs& a, int nsets, const void* const* packed, c
   MmArgs a0 = a;
   a0.qzeros = qzeros[0];
   return launch_decode_sets(a0, sets);
+}
+
+// ---- MoE decode: one token, top_k experts chosen on the device (DecSets::moe; b2q_moe_decode_*) -------------------------
+// The grouped small-batch kernels (b2q_midm.cu MODE 1 / 2) serve a single token at ~1 TB/s (tcgen05 tiles of >= 16 token
+// columns, 56 - 128 CTAs); the decode tier streams the same bytes 2 - 3x faster.  gate | up: the 2 * top_k (expert, w1 | w3)
+// matrices are virtual sibling sets of ONE decode launch over the same activations.  down: a cluster of top_k CTAs per tile
+// column, rank r multiplying pair r's activations with ITS expert's w2; the DSMEM reduction applies the routing weights.
+static void moe_strides(DecSets& sets, int K, int N, int group_size) {
+  const size_t G = (size_t)K / (size_t)group_size;
+  sets.estride_w = (size_t)K * (size_t)N / 2 / 16;  // uint4
+  sets.estride_s = G * (size_t)N;                   // elements
+  sets.estride_z = G * (size_t)N / 8;               // uint32
+}
+
+int launch_moe_decode_gate_up(const MmArgs& a, const void* packed1, const void* scales1, const int32_t* qzeros1,
+                              const void* packed3, const void* scales3, const int32_t* qzeros3, const int32_t* ids,
+                              int top_k, int E, void* gu) {
+  if (!decode_supported(a) || a.M != 1 || top_k < 1 || top_k > 8 || (qzeros1 != nullptr) != (qzeros3 != nullptr)) {
+    set_error("b2q_moe_decode_gate_up: needs one token, bits=4, K %% 128 == 0, group_size 64|128|K, 1 <= top_k <= 8 "
+              "(M=%d K=%d N=%d g=%d top_k=%d)", a.M, a.K, a.N, a.group_size, top_k);
+    return -1;
+  }
+  DecSets sets = {};
+  sets.nsets = 1;
+  const int tiles = 2 * top_k * (a.N / 32);
+  for (int i = 0; i < DEC_MAX_SETS; ++i) sets.tile_end[i] = tiles;
+  sets.N[0] = a.N;
+  sets.packed[0] = (const uint4*)packed1;
+  sets.packed[1] = (const uint4*)packed3;
+  sets.scales[0] = scales1;
+  sets.scales[1] = scales3;
+  sets.qzeros[0] = (const uint32_t*)qzeros1;
+  sets.qzeros[1] = (const uint32_t*)qzeros3;
+  sets.out[0] = gu;
+  sets.moe = 1;
+  sets.nexperts = E;
+  sets.ids = ids;
+  moe_strides(sets, a.K, a.N, a.group_size);
+  MmArgs a0 = a;
+  a0.qzeros = qzeros1;
+  a0.perm = nullptr;
+  a0.bias = nullptr;
+  a0.out = gu;
+  return launch_decode_sets(a0, sets);
+}
+
+int launch_moe_decode_down(const MmArgs& a, const int32_t* ids, const float* wts, int top_k, int E) {
+  if (!decode_supported(a) || a.M != 1 || !(top_k == 2 || top_k == 4 || top_k == 8)) {
+    set_error("b2q_moe_decode_down: needs one token, bits=4, K %% 128 == 0, group_size 64|128|K, top_k 2|4|8 (M=%d K=%d N=%d "
+              "g=%d top_k=%d)", a.M, a.K, a.N, a.group_size, top_k);
+    return -1;
+  }
+  DecSets sets = {};
+  sets.nsets = 1;
+  const int NT = a.N / 32;
+  for (int i = 0; i < DEC_MAX_SETS; ++i) sets.tile_end[i] = NT;
+  sets.N[0] = a.N;
+  sets.packed[0] = (const uint4*)a.packed;
+  sets.scales[0] = a.scales;
+  sets.qzeros[0] = (const uint32_t*)a.qzeros;
+  sets.out[0] = a.out;
+  sets.moe = 2;
+  sets.nexperts = E;
+  sets.ids = ids;
+  sets.wts = wts;
+  moe_strides(sets, a.K, a.N, a.group_size);
+  DecodeCfg c = {};
+  c.ks = top_k;
+  c.warps = DEC_MAX_WARPS;
+  c.ngroups = 1;
+  c.qpc = a.K / 128;  // a rank's k-range is its expert's whole K
+  c.C = 148 / top_k;
+  if (c.C > NT) c.C = NT;
+  c.max_tiles = (NT + c.C - 1) / c.C;
+  c.stl = 2;
+  c.smem = decode_smem(1, c.warps, c.qpc, c.max_tiles, 4);
+  if (c.smem > 200 * 1024) {
+    c.stl = 1;
+    c.smem = decode_smem(1, c.warps, c.qpc, c.max_tiles, 2);
+  }
+  if (c.smem > 200 * 1024) {
+    set_error("b2q_moe_decode_down: K=%d does not fit shared memory", a.K);
+    return -1;
+  }
+  MmArgs a0 = a;
+  a0.perm = nullptr;
+  a0.bias = nullptr;
+  const bool asym = a.qzeros != nullptr, g64 = a.group_size == 64;
+  const DecodeAR none = {};
+#define B2Q_DEC_CASE(T)                                                            \
+  (asym ? (g64 ? launch_decode_t<T, true, true, true>(a0, sets, c, none)           \
+               : launch_decode_t<T, true, false, true>(a0, sets, c, none))         \
+        : (g64 ? launch_decode_t<T, false, true, true>(a0, sets, c, none)          \
+               : launch_decode_t<T, false, false, true>(a0, sets, c, none)))
+  return a.dtype == 0 ? B2Q_DEC_CASE(__half) : B2Q_DEC_CASE(__nv_bfloat16);
+#undef B2Q_DEC_CASE
 }
 
 }  // namespace b2q

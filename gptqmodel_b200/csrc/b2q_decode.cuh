@@ -215,6 +215,18 @@ struct DecSets {
   const uint32_t* qzeros[DEC_MAX_SETS];
   const void* bias[DEC_MAX_SETS];
   void* out[DEC_MAX_SETS];
+  // MoE decode: ONE token, its top_k experts picked on the device (b2q_moe_decode_*; no host synchronisation).
+  //   moe = 1 (gate | up)  tile gt -> virtual set s = gt / (N[0] / 32): expert ids[s >> 1], weights of stack packed[s & 1]
+  //                        (0: w1, 1: w3), output row s of out[0] ([2 * top_k, N]); every set reads the same activations;
+  //   moe = 2 (down)       cluster rank r = pair r of the token: expert ids[r], the rank's k-range is the expert's WHOLE K,
+  //                        its activations are row r of x ([top_k, K]), and the DSMEM reduction sums wts[r] * T(rank r's
+  //                        output) — y = sum_j w_j * w2_e(h_j) with the module's rounding, in one launch.
+  // ids are data of an earlier kernel: a moe launch executes griddepcontrol.wait BEFORE its first expert-dependent address.
+  int moe;
+  int nexperts;
+  const int32_t* ids;
+  const float* wts;
+  size_t estride_w, estride_s, estride_z;  // expert strides of the stacks in uint4 / elements / uint32
 };
 
 template <typename T>
@@ -227,8 +239,31 @@ struct TileRef {
   int N, nt;
 };
 
-template <typename T>
+template <typename T, bool MOE = false>
 __device__ __forceinline__ TileRef<T> resolve_tile(const DecSets& S, int gt) {
+  TileRef<T> r;
+  if (MOE) {
+    int s = 0, nt = gt, slot;
+    if (S.moe == 1) {
+      const int nts = S.N[0] >> 5;
+      s = gt / nts;
+      nt = gt - s * nts;
+      slot = s >> 1;
+    } else {
+      slot = (int)cluster_ctarank();
+    }
+    int e = S.ids[slot];
+    e = e < 0 ? 0 : (e >= S.nexperts ? S.nexperts - 1 : e);  // a corrupt id must not become a wild pointer
+    const int b = (S.moe == 1) ? (s & 1) : 0;
+    r.w = S.packed[b] + (size_t)e * S.estride_w;
+    r.sc = reinterpret_cast<const T*>(S.scales[b]) + (size_t)e * S.estride_s;
+    r.zq = S.qzeros[b] != nullptr ? S.qzeros[b] + (size_t)e * S.estride_z : nullptr;
+    r.bias = nullptr;
+    r.out = reinterpret_cast<T*>(S.out[0]) + (S.moe == 1 ? (size_t)s * S.N[0] : 0);
+    r.N = S.N[0];
+    r.nt = nt;
+    return r;
+  }
   int s = 0, start = 0;
   if (S.nsets > 1 && gt >= S.tile_end[0]) {
     s = 1;
@@ -238,7 +273,6 @@ __device__ __forceinline__ TileRef<T> resolve_tile(const DecSets& S, int gt) {
       start = S.tile_end[1];
     }
   }
-  TileRef<T> r;
   r.w = S.packed[s];
   r.sc = reinterpret_cast<const T*>(S.scales[s]);
   r.zq = S.qzeros[s];

@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t dec_ld_acquire_sys(const uint32_t* p) {
 // dynamic smem: ring[nwarps][nst][2 KB] | sx[M][kspan] (T) | xsum[qpc * 2][8] f32 |
 //               wpart[ngroups][max_tiles][M][gw][32] f32 | cpart[ngroups][max_tiles][M][32] f32 (split-K only) |
 //               mbarriers[nwarps][DEC_STAGES] + 1 (activations)
-template <typename T, bool ASYM, bool G64>
+template <typename T, bool ASYM, bool G64, bool MOE>
 __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     decode2_kernel(const __grid_constant__ DecSets S, const int32_t* __restrict__ perm, const T* __restrict__ x, int M,
                    int K, int gsh, int qpc, int max_tiles, int gw, int stl, int xtma,
@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
     }
   };
   stamp(0);
+  // MoE decode (DecSets::moe == 1): expert ids are data of an earlier kernel — wait before the first expert-dependent address
+  if (MOE) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int ngroups = nwarps / gw;               // independent warp groups; a group owns whole tiles
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   size_t iss_kbs = 0;
   int iss_q = 0, iss_u = 0, iss_ti = 0;
   auto iss_begin_tile = [&]() {
-    const TileRef<T> r = resolve_tile<T>(S, tile0 + iss_ti * C);
+    const TileRef<T> r = resolve_tile<T, MOE>(S, tile0 + iss_ti * C);
     iss_kbs = (size_t)(r.N >> 4) * 32;
     iss_src = r.w + (size_t)(2 * (q0 + wg)) * iss_kbs + (size_t)(2 * r.nt) * 32;
   };
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const uint32_t* zq_next = nullptr;
   int pre_q = 0, pre_ti = 0, pre_N = 0;
   auto pre_begin_tile = [&]() {
-    const TileRef<T> r = resolve_tile<T>(S, tile0 + pre_ti * C);
+    const TileRef<T> r = resolve_tile<T, MOE>(S, tile0 + pre_ti * C);
     pre_N = r.N;
     sc_next = r.sc + (size_t)g_first * r.N + r.nt * 32 + g;
     if (ASYM) zq_next = r.zq + (size_t)g_first * (r.N >> 3) + r.nt * 4;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   auto row_ref = [&](int row) {  // row = (group, tile, token); lane = feature inside the 32-feature tile
     const int m = row % M, r2 = row / M;
     const int ti = r2 % max_tiles, g2 = r2 / max_tiles;
-    const TileRef<T> tr = resolve_tile<T>(S, (int)blockIdx.x * ngroups + g2 + ti * C);
+    const TileRef<T> tr = resolve_tile<T, MOE>(S, (int)blockIdx.x * ngroups + g2 + ti * C);
     const int n = tr.nt * 32 + lane;
     RowRef r;
     r.out = tr.out;
@@ -524,9 +526,9 @@ bool decode2_plan(const MmArgs& a, int NT, int* out8) {
   return true;
 }
 
-template <typename T, bool ASYM, bool G64>
+template <typename T, bool ASYM, bool G64, bool MOE = false>
 static int launch_decode2_t(const MmArgs& a, const DecSets& sets, const Decode2Cfg& c, const DecodeAR& ar) {
-  auto kern = decode2_kernel<T, ASYM, G64>;
+  auto kern = decode2_kernel<T, ASYM, G64, MOE>;
   if (c.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return (int)e;
@@ -560,12 +562,13 @@ static int launch_decode2_ar(const MmArgs& a, const DecSets& sets, const DecodeA
   if (!decode2_config(a, sets.tile_end[sets.nsets - 1], c)) return -2;
   if (ar.world > 1 && c.C * c.ks > DEC_AR_MAXCTA) return -2;
   const bool asym = a.qzeros != nullptr, g64 = a.group_size == 64;
-#define B2Q_DEC2_CASE(T)                                                          \
-  (asym ? (g64 ? launch_decode2_t<T, true, true>(a, sets, c, ar)                      \
-               : launch_decode2_t<T, true, false>(a, sets, c, ar))                    \
-        : (g64 ? launch_decode2_t<T, false, true>(a, sets, c, ar)                     \
-               : launch_decode2_t<T, false, false>(a, sets, c, ar)))
-  return a.dtype == 0 ? B2Q_DEC2_CASE(__half) : B2Q_DEC2_CASE(__nv_bfloat16);
+#define B2Q_DEC2_CASE(T, MOE)                                                          \
+  (asym ? (g64 ? launch_decode2_t<T, true, true, MOE>(a, sets, c, ar)                      \
+               : launch_decode2_t<T, true, false, MOE>(a, sets, c, ar))                    \
+        : (g64 ? launch_decode2_t<T, false, true, MOE>(a, sets, c, ar)                     \
+               : launch_decode2_t<T, false, false, MOE>(a, sets, c, ar)))
+  if (sets.moe != 0) return a.dtype == 0 ? B2Q_DEC2_CASE(__half, true) : B2Q_DEC2_CASE(__nv_bfloat16, true);
+  return a.dtype == 0 ? B2Q_DEC2_CASE(__half, false) : B2Q_DEC2_CASE(__nv_bfloat16, false);
 #undef B2Q_DEC2_CASE
 }
 

@@ -111,4 +111,45 @@ int launch_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int
   return (int)cudaGetLastError();
 }
 
+// MoE decode (one token): h[j, n] = T(T(silu(g)) * u) with g = gu[2j, n], u = gu[2j + 1, n] — the rounding points of the
+// reference's per-expert module loop (act_fn(w1(x)) * w3(x) on 16-bit tensors), as in midm_kernel<MODE 1>'s epilogue.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    moe_decode_act_kernel(const T* __restrict__ gu, T* __restrict__ h, int top_k, int N) {
+  using E = ET<T>;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int j = blockIdx.y;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (n >= N) return;
+  const uint32_t gw = *reinterpret_cast<const uint32_t*>(gu + (size_t)(2 * j) * N + n);
+  const uint32_t uw = *reinterpret_cast<const uint32_t*>(gu + (size_t)(2 * j + 1) * N + n);
+  const T* gp = reinterpret_cast<const T*>(&gw);
+  const T* up = reinterpret_cast<const T*>(&uw);
+  float hv[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float gq = E::to_f(gp[i]), uq = E::to_f(up[i]);
+    const float aq = E::to_f(E::from_f(gq / (1.f + __expf(-gq))));
+    hv[i] = aq * uq;
+  }
+  *reinterpret_cast<uint32_t*>(h + (size_t)j * N + n) = E::pack2(hv[0], hv[1]);
+}
+
+int launch_moe_decode_act(const void* gu, void* h, int top_k, int N, int dtype, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((N / 2 + 255) / 256, top_k, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env().disable_pdl ? 0 : 1;
+  if (dtype == 0)
+    return (int)cudaLaunchKernelEx(&cfg, moe_decode_act_kernel<__half>, (const __half*)gu, (__half*)h, top_k, N);
+  return (int)cudaLaunchKernelEx(&cfg, moe_decode_act_kernel<__nv_bfloat16>, (const __nv_bfloat16*)gu, (__nv_bfloat16*)h,
+                                 top_k, N);
+}
+
 }  // namespace b2q

@@ -5,6 +5,9 @@ In the reference every expert's ``w1 / w3 / w2`` is an independent QuantLinear m
 fused MoE kernel it ships (``swordfish_moe.cu``) is exported but never called.  This module is that
 per-expert loop, arranged for the B200 kernels and for tensor parallelism:
 
+  * ONE TOKEN (batch-1 decode) through grouped-eligible experts: three launches on the decode tier — the 2 * top_k gate / up
+    matrices as sibling sets of one decode launch (experts read from `topk_ids` on the device), SiLU-mul, and a cluster of
+    top_k CTAs per tile column for w2 whose DSMEM reduction applies the routing weights (`b2q_moe_decode_*`);
   * GROUPED path (default whenever every expert is a 4-bit B200 QuantLinear of one shape): the (token, k) pairs are sorted
     by expert ON THE DEVICE (`b2q_moe_align`), and the whole block is five launches with no host synchronisation —
     align, gather, ONE grouped launch for w1 and w3 with the SiLU-mul epilogue, ONE grouped launch for w2 with the routing
@@ -49,6 +52,7 @@ class MoEExperts(torch.nn.Module):
         self.w1, self.w3, self.w2 = as_list(w1), as_list(w3), as_list(w2)
         self.group = group
         self.reduce = reduce  # optional tp.P2PAllReduce for decode-sized outputs
+        self.decode_path = True  # one token: the decode-tier launches (False: always the grouped small-batch kernels; A/B)
         self._stack = None
         if grouped is None or grouped:
             self._stack = self._build_stack()
@@ -119,6 +123,20 @@ class MoEExperts(torch.nn.Module):
         K, inter, Kout = s1["K"], s1["N"], s2["N"]
         ids = topk_ids.to(torch.int32).contiguous()
         wts = topk_weights.to(torch.float32).contiguous()
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        if T == 1 and self.decode_path and self._decode_ok(top_k):
+            # batch-1 decode: the token's top_k experts on the decode tier, three launches (include/b2q.h: b2q_moe_decode_*)
+            x2 = x.contiguous()
+            gu = torch.empty((2 * top_k, inter), dtype=dt, device=dev)
+            h = torch.empty((top_k, inter), dtype=dt, device=dev)
+            y = torch.empty((1, Kout), dtype=dt, device=dev)
+            check(lib.b2q_moe_decode_gate_up(p(x2), p(s1["packed"]), p(self._scales("w1", dt)), p(s1["zeros"]),
+                                             p(s3["packed"]), p(self._scales("w3", dt)), p(s3["zeros"]), p(ids), top_k, E, K,
+                                             inter, 4, s1["group"], code, p(gu), st), "b2q_moe_decode_gate_up")
+            check(lib.b2q_moe_decode_act(p(gu), p(h), top_k, inter, code, st), "b2q_moe_decode_act")
+            check(lib.b2q_moe_decode_down(p(h), p(s2["packed"]), p(self._scales("w2", dt)), p(s2["zeros"]), p(ids), p(wts),
+                                          top_k, E, inter, Kout, 4, s2["group"], code, p(y), st), "b2q_moe_decode_down")
+            return y
         tables = torch.empty(2 * E + rows, dtype=torch.int32, device=dev)
         counts, offsets, sorted_pairs = tables[:E], tables[E:2 * E], tables[2 * E:]
         x2 = x.contiguous()
@@ -126,7 +144,6 @@ class MoEExperts(torch.nn.Module):
         h = torch.empty((rows, inter), dtype=dt, device=dev)
         ypair = torch.empty((rows, Kout), dtype=torch.float32, device=dev)
         y = torch.empty((T, Kout), dtype=dt, device=dev)
-        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         active = min(E, rows)
         check(lib.b2q_moe_align(p(ids), T, top_k, E, p(counts), p(offsets), p(sorted_pairs), st), "b2q_moe_align")
         check(lib.b2q_moe_gather(p(x2), p(sorted_pairs), p(xs), rows, top_k, K, st), "b2q_moe_gather")
@@ -138,6 +155,14 @@ class MoEExperts(torch.nn.Module):
               "b2q_moe_down")
         check(lib.b2q_moe_combine(p(ypair), p(y), T, top_k, Kout, code, st), "b2q_moe_combine")
         return y
+
+    def _decode_ok(self, top_k: int) -> bool:
+        """The decode tier's envelope for the one-token path: K % 128 == 0 on both matmuls, group_size 64 / 128 / K,
+        top_k in {2, 4, 8} (cluster size of the down launch)."""
+        s1, s2 = self._stack["w1"], self._stack["w2"]
+        ok_g = lambda s: s["group"] in (64, 128, s["K"])  # noqa: E731
+        return (top_k in (2, 4, 8) and s1["K"] % 128 == 0 and s2["K"] % 128 == 0 and s1["N"] % 32 == 0
+                and s2["N"] % 32 == 0 and ok_g(s1) and ok_g(s2))
 
     @property
     def num_experts(self) -> int:

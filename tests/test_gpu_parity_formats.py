@@ -210,3 +210,64 @@ def test_tiny_llama_with_b200_quantlinears_on_gpu():
             b = dense(ids).logits.float()
         assert a.shape == shape + (1000,) and torch.isfinite(a).all()
         assert (a - b).abs().max().item() < 3e-2 * b.abs().max().item(), shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sym,gs", [(False, 64), (True, 128)])
+def test_moe_one_token_decode_path(sym, gs):
+    """Batch-1 decode through the experts on the decode tier (b2q_moe_decode_*): Mixtral TP-4 shard shapes (4096 x 3584 /
+    3584 x 4096), top-2 of 8 experts, against the grouped small-batch kernels on the same stack and the oracle; the expert ids
+    are read on the device, so a captured graph follows new routing decisions."""
+    import torch.nn.functional as F
+    from gptqmodel_b200 import B200QuantLinear, moe
+    from helpers import random_layer
+    E, K, I, top_k = 8, 4096, 3584, 2
+    mk = lambda L: B200QuantLinear.from_checkpoint_tensors(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], 4, gs,  # noqa: E731
+                                                           sym=sym)
+    Ls = [(random_layer(K, I, group_size=gs, sym=sym, seed=3 * e, device="cuda"),
+           random_layer(K, I, group_size=gs, sym=sym, seed=3 * e + 1, device="cuda"),
+           random_layer(I, K, group_size=gs, sym=sym, seed=3 * e + 2, device="cuda")) for e in range(E)]
+    blk = moe.MoEExperts([mk(l[0]) for l in Ls], [mk(l[1]) for l in Ls], [mk(l[2]) for l in Ls])
+    assert blk._stack is not None and blk._decode_ok(top_k)
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.randn(1, K, generator=gen) * 0.2).to(torch.float16).cuda()
+
+    def oracle_block(ids, w):
+        ref = torch.zeros(1, K, dtype=torch.float64)
+        for j in range(top_k):
+            l1, l3, l2 = Ls[int(ids[0, j])]
+            W1, W3, W2 = (oracle.dequantize_weight(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], 4).float() for L in (l1, l3, l2))
+            g = (x.float() @ W1).to(torch.float16)
+            u = (x.float() @ W3).to(torch.float16)
+            h = (F.silu(g.float()).to(torch.float16).float() * u.float()).to(torch.float16)
+            ref += float(w[0, j]) * (h.float() @ W2).to(torch.float16).double().cpu()
+        return ref.float()
+
+    for trial in range(3):
+        ids, w = moe.route_topk(torch.randn(1, E, generator=gen), top_k)
+        blk.decode_path = True
+        y_dec = blk(x, ids.cuda(), w.cuda())
+        blk.decode_path = False
+        y_grp = blk(x, ids.cuda(), w.cuda())
+        ref = oracle_block(ids, w)
+        assert_close_rel(y_dec, ref, 4e-3, f"moe decode path trial {trial}")
+        assert_close_rel(y_grp, ref, 4e-3, f"moe grouped path trial {trial}")
+        assert_close_rel(y_dec, y_grp, 4e-3, f"moe decode vs grouped trial {trial}")
+    # CUDA graph: the routing tensors are inputs, not constants
+    blk.decode_path = True
+    idc, wc = ids.cuda(), w.cuda()
+    s_ = torch.cuda.Stream()
+    s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        blk(x, idc, wc)
+    torch.cuda.current_stream().wait_stream(s_)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        yg = blk(x, idc, wc)
+    ids2, w2 = moe.route_topk(torch.randn(1, E, generator=gen), top_k)
+    idc.copy_(ids2)
+    wc.copy_(w2)
+    gr.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(yg, blk(x, ids2.cuda(), w2.cuda()))
+    assert_close_rel(yg, oracle_block(ids2, w2), 4e-3, "moe decode path, graph replay with new routing")
