@@ -41,7 +41,7 @@ SYMBOLS = {
     "b2q_moe_combine": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b2q_moe_decode_gate_up": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b2q_moe_decode_act": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "b2q_moe_decode_down": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b2q_moe_decode_down": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 

@@ -520,7 +520,7 @@ int b2q_moe_decode_act(const void* gu, void* h, int top_k, int N, int dtype, voi
 
 int b2q_moe_decode_down(const void* h, const void* packed2, const void* scales2, const int32_t* qzeros2,
                         const int32_t* topk_ids, const float* topk_weights, int top_k, int E, int K, int N, int bits,
-                        int group_size, int dtype, void* y, void* stream) {
+                        int group_size, int dtype, int fused_act, void* y, void* stream) {
   int v = validate("b2q_moe_decode_down", h, packed2, scales2, y, 1, K, N, bits, group_size, dtype);
   if (v != 0) return v;
   if (topk_ids == nullptr || topk_weights == nullptr || E < 1) {
@@ -530,7 +530,7 @@ int b2q_moe_decode_down(const void* h, const void* packed2, const void* scales2,
   DeviceGuard dg(packed2);
   MmArgs a = make_args(h, packed2, scales2, qzeros2, nullptr, nullptr, y, 1, K, N, bits, group_size, dtype, nullptr, 0,
                        stream);
-  return check_cuda(launch_moe_decode_down(a, topk_ids, topk_weights, top_k, E), "b2q_moe_decode_down");
+  return check_cuda(launch_moe_decode_down(a, topk_ids, topk_weights, top_k, E, fused_act), "b2q_moe_decode_down");
 }
 
 }  // extern "C"

@@ -61,10 +61,10 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   const int ntiles = (tile0 < TT) ? (TT - tile0 + C - 1) / C : 0;  // tiles of this group
   const int nquads = K >> 7;
   // moe == 2: every cluster rank owns a whole expert (k-range 0 .. K of ITS weights) and its own row of activations
-  const int q0 = (MOE && S.moe == 2) ? 0 : blockIdx.y * qpc;
+  const int q0 = (MOE && S.moe >= 2) ? 0 : blockIdx.y * qpc;
   const int q1 = min(q0 + qpc, nquads);
   const int kspan = qpc * 128;
-  if (MOE && S.moe == 2) x += (size_t)blockIdx.y * K;
+  if (MOE && S.moe >= 2) x += (size_t)blockIdx.y * K * (S.moe == 3 ? 2 : 1);  // row r (or rows 2r, 2r + 1) of the rank
   const int nst = 1 << stl;  // ring stages per warp (2 or 4)
   uint8_t* ring = dsm + (size_t)warp * nst * DEC_QUAD_BYTES;
   T* sx = reinterpret_cast<T*>(dsm + (size_t)nwarps * nst * DEC_QUAD_BYTES);
@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
   // A thread's loads (up to SX_UNROLL x 16 bytes, K = 14336 needs 3.5 per thread) are all issued BEFORE the first is
   // consumed: the rolled loop paid one dependent L2 round trip per iteration (2.6 us of the 11 us down_proj launch,
   // profiles/r02_decode_notes.md).
-  if (OWN) {
+  if (MOE && S.moe == 3) {
+    stage_x_own_quads<T, true>(x, sx, xsum, 1, K, q0, nq, wg, gw, kspan);
+  } else if (OWN) {
     stage_x_own_quads<T>(x, sx, xsum, M, K, q0, nq, wg, gw, kspan);
   } else if (PERM) {
     stage_x_act_order<T>(x, perm + K, sx, xsum, M, K, q0 * 128, (q1 - q0) * 128, kspan);
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(DEC_MAX_WARPS * 32)
           for (uint32_t r = 0; r < nrank; ++r) {
             float pr = ld_dsmem_f32(smem_u32(&part[(grp * max_tiles + ti) * 256 + i]), r);
             // MoE down: rank r holds expert r's complete output: y_r = T(h_r W2) like the module, then the routing weight
-            if (MOE && S.moe == 2) pr = S.wts[r] * E::to_f(E::from_f(pr));
+            if (MOE && S.moe >= 2) pr = S.wts[r] * E::to_f(E::from_f(pr));
             v += pr;
           }
           const int n = nt * 32 + (acc >> 2) * 16 + (ln >> 2) + ((acc & 2) ? 8 : 0);
@@ -684,7 +686,7 @@ int launch_moe_decode_gate_up(const MmArgs& a, const void* packed1, const void* 
   return launch_decode_sets(a0, sets);
 }
 
-int launch_moe_decode_down(const MmArgs& a, const int32_t* ids, const float* wts, int top_k, int E) {
+int launch_moe_decode_down(const MmArgs& a, const int32_t* ids, const float* wts, int top_k, int E, int fused_act) {
   if (!decode_supported(a) || a.M != 1 || !(top_k == 2 || top_k == 4 || top_k == 8)) {
     set_error("b2q_moe_decode_down: needs one token, bits=4, K %% 128 == 0, group_size 64|128|K, top_k 2|4|8 (M=%d K=%d N=%d "
               "g=%d top_k=%d)", a.M, a.K, a.N, a.group_size, top_k);
@@ -699,7 +701,7 @@ int launch_moe_decode_down(const MmArgs& a, const int32_t* ids, const float* wts
   sets.scales[0] = a.scales;
   sets.qzeros[0] = (const uint32_t*)a.qzeros;
   sets.out[0] = a.out;
-  sets.moe = 2;
+  sets.moe = fused_act ? 3 : 2;
   sets.nexperts = E;
   sets.ids = ids;
   sets.wts = wts;

@@ -159,7 +159,9 @@ __device__ __forceinline__ void zero_own_xsum_padding(float* xsum, int M, int nq
   }
 }
 
-template <typename T>
+// SILU: the activations are h = T(T(silu(g)) * u) of two rows g = x, u = x + K computed while staging (MoE down launch with
+// the SiLU-mul of the reference's module boundary folded in: midm_kernel<MODE 1>'s epilogue arithmetic); one token only.
+template <typename T, bool SILU = false>
 __device__ __forceinline__ void stage_x_own_quads(const T* __restrict__ x, T* sx, float* xsum, int M, int K, int q0, int nq,
                                                   int wg, int gw, int kspan) {
   using E = ET<T>;
@@ -172,12 +174,13 @@ __device__ __forceinline__ void stage_x_own_quads(const T* __restrict__ x, T* sx
     return E::to_f(h[0]) + E::to_f(h[1]);
   };
   for (int v0 = 0; v0 < units; v0 += U) {
-    uint4 xv[U];
+    uint4 xv[U], uv[U];
     int mm[U], ql[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int v = v0 + u;
       xv[u] = make_uint4(0, 0, 0, 0);
+      uv[u] = make_uint4(0, 0, 0, 0);
       mm[u] = 0;
       ql[u] = -1;
       if (v < units) {
@@ -187,6 +190,30 @@ __device__ __forceinline__ void stage_x_own_quads(const T* __restrict__ x, T* sx
           mm[u] = m;
           ql[u] = wg + qi * gw;
           xv[u] = reinterpret_cast<const uint4*>(x + (size_t)m * K + (size_t)q0 * 128)[ql[u] * 16 + j];
+          if (SILU) uv[u] = reinterpret_cast<const uint4*>(x + (size_t)K + (size_t)q0 * 128)[ql[u] * 16 + j];
+        }
+      }
+    }
+    if (SILU) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ql[u] >= 0) {
+          uint32_t gw4[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+          const uint32_t uw4[4] = {uv[u].x, uv[u].y, uv[u].z, uv[u].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const T* gp = reinterpret_cast<const T*>(&gw4[c]);
+            const T* up = reinterpret_cast<const T*>(&uw4[c]);
+            float hv[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float gq = E::to_f(gp[i]), uq = E::to_f(up[i]);
+              const float aq = E::to_f(E::from_f(gq / (1.f + __expf(-gq))));
+              hv[i] = aq * uq;
+            }
+            gw4[c] = E::pack2(hv[0], hv[1]);
+          }
+          xv[u] = make_uint4(gw4[0], gw4[1], gw4[2], gw4[3]);
         }
       }
     }
@@ -220,7 +247,9 @@ struct DecSets {
   //                        (0: w1, 1: w3), output row s of out[0] ([2 * top_k, N]); every set reads the same activations;
   //   moe = 2 (down)       cluster rank r = pair r of the token: expert ids[r], the rank's k-range is the expert's WHOLE K,
   //                        its activations are row r of x ([top_k, K]), and the DSMEM reduction sums wts[r] * T(rank r's
-  //                        output) — y = sum_j w_j * w2_e(h_j) with the module's rounding, in one launch.
+  //                        output) — y = sum_j w_j * w2_e(h_j) with the module's rounding, in one launch;
+  //   moe = 3 (down + act) as 2, but x is the gate | up buffer [2 * top_k, K] of moe = 1 and rank r stages
+  //                        h = T(T(silu(x[2r])) * x[2r + 1]) itself: the SiLU-mul launch disappears.
   // ids are data of an earlier kernel: a moe launch executes griddepcontrol.wait BEFORE its first expert-dependent address.
   int moe;
   int nexperts;

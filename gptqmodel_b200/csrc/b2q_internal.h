@@ -72,7 +72,7 @@ int launch_moe_decode_gate_up(const MmArgs& a, const void* packed1, const void* 
                               const void* packed3, const void* scales3, const int32_t* qzeros3, const int32_t* ids,
                               int top_k, int E, void* gu);                                      // b2q_decode.cu
 int launch_moe_decode_act(const void* gu, void* h, int top_k, int N, int dtype, cudaStream_t stream);  // b2q_moe.cu
-int launch_moe_decode_down(const MmArgs& a, const int32_t* ids, const float* wts, int top_k, int E);   // b2q_decode.cu
+int launch_moe_decode_down(const MmArgs& a, const int32_t* ids, const float* wts, int top_k, int E, int fused_act);  // b2q_decode.cu
 int launch_gemm2(const MmArgs& a, const void* x);
 int launch_gemm2_multi(const MmArgs& a, const void* x, int nsets, const void* const* packed, const void* const* scales,
                        const int32_t* const* qzeros, const void* const* bias, void* const* out, const int* Ns);

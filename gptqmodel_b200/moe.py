@@ -53,6 +53,7 @@ class MoEExperts(torch.nn.Module):
         self.group = group
         self.reduce = reduce  # optional tp.P2PAllReduce for decode-sized outputs
         self.decode_path = True  # one token: the decode-tier launches (False: always the grouped small-batch kernels; A/B)
+        self.fuse_act = True     # ... with the SiLU-mul folded into the down launch's activation staging (False: own launch)
         self._stack = None
         if grouped is None or grouped:
             self._stack = self._build_stack()
@@ -133,9 +134,14 @@ class MoEExperts(torch.nn.Module):
             check(lib.b2q_moe_decode_gate_up(p(x2), p(s1["packed"]), p(self._scales("w1", dt)), p(s1["zeros"]),
                                              p(s3["packed"]), p(self._scales("w3", dt)), p(s3["zeros"]), p(ids), top_k, E, K,
                                              inter, 4, s1["group"], code, p(gu), st), "b2q_moe_decode_gate_up")
+            if self.fuse_act:  # SiLU-mul computed by the down launch while it stages its activations: two launches
+                check(lib.b2q_moe_decode_down(p(gu), p(s2["packed"]), p(self._scales("w2", dt)), p(s2["zeros"]), p(ids),
+                                              p(wts), top_k, E, inter, Kout, 4, s2["group"], code, 1, p(y), st),
+                      "b2q_moe_decode_down")
+                return y
             check(lib.b2q_moe_decode_act(p(gu), p(h), top_k, inter, code, st), "b2q_moe_decode_act")
             check(lib.b2q_moe_decode_down(p(h), p(s2["packed"]), p(self._scales("w2", dt)), p(s2["zeros"]), p(ids), p(wts),
-                                          top_k, E, inter, Kout, 4, s2["group"], code, p(y), st), "b2q_moe_decode_down")
+                                          top_k, E, inter, Kout, 4, s2["group"], code, 0, p(y), st), "b2q_moe_decode_down")
             return y
         tables = torch.empty(2 * E + rows, dtype=torch.int32, device=dev)
         counts, offsets, sorted_pairs = tables[:E], tables[E:2 * E], tables[2 * E:]

@@ -134,7 +134,9 @@ int b2q_moe_combine(const float* ypair, void* y, int T, int top_k, int N, int dt
  *   b2q_moe_decode_act     : h [top_k, N]    <- T(T(silu(gu[2j])) * gu[2j+1])                      (module rounding points)
  *   b2q_moe_decode_down    : y [1, N]        <- sum_j topk_weights[j] * T(h[j] W2_e): a cluster of top_k CTAs per tile column,
  *                            rank j multiplies row j with ITS expert's w2 (K = intermediate size), the reduction through
- *                            distributed shared memory applies the routing weights; one rounding      (top_k in {2, 4, 8})
+ *                            distributed shared memory applies the routing weights; one rounding      (top_k in {2, 4, 8}).
+ *                            fused_act = 1: `h` is the gu buffer itself and every rank computes its row of h while staging
+ *                            the activations (same arithmetic as b2q_moe_decode_act) — two launches per block
  * 4-bit, K % 128 == 0, group_size 64 | 128 | K (the decode tier's envelope). */
 int b2q_moe_decode_gate_up(const void* x, const void* packed1, const void* scales1, const int32_t* qzeros1,
                            const void* packed3, const void* scales3, const int32_t* qzeros3, const int32_t* topk_ids,
@@ -142,7 +144,7 @@ int b2q_moe_decode_gate_up(const void* x, const void* packed1, const void* scale
 int b2q_moe_decode_act(const void* gu, void* h, int top_k, int N, int dtype, void* stream);
 int b2q_moe_decode_down(const void* h, const void* packed2, const void* scales2, const int32_t* qzeros2,
                         const int32_t* topk_ids, const float* topk_weights, int top_k, int E, int K, int N, int bits,
-                        int group_size, int dtype, void* y, void* stream);
+                        int group_size, int dtype, int fused_act, void* y, void* stream);
 
 /* In-place all-reduce(sum) of a small 16-bit vector (n % 8 == 0, n <= max_elems) across `world` <= 8 GPUs of one
  * NVLink domain: the single collective of a row-parallel QuantLinear at decode time (the reference has

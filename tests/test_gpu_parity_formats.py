@@ -245,8 +245,11 @@ def test_moe_one_token_decode_path(sym, gs):
 
     for trial in range(3):
         ids, w = moe.route_topk(torch.randn(1, E, generator=gen), top_k)
-        blk.decode_path = True
+        blk.decode_path, blk.fuse_act = True, True
         y_dec = blk(x, ids.cuda(), w.cuda())
+        blk.fuse_act = False     # SiLU-mul as its own launch: the same arithmetic, hence the same bits
+        assert torch.equal(blk(x, ids.cuda(), w.cuda()), y_dec)
+        blk.fuse_act = True
         blk.decode_path = False
         y_grp = blk(x, ids.cuda(), w.cuda())
         ref = oracle_block(ids, w)
