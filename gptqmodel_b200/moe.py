@@ -53,7 +53,10 @@ class MoEExperts(torch.nn.Module):
         self.group = group
         self.reduce = reduce  # optional tp.P2PAllReduce for decode-sized outputs
         self.decode_path = True  # one token: the decode-tier launches (False: always the grouped small-batch kernels; A/B)
-        self.fuse_act = True     # ... with the SiLU-mul folded into the down launch's activation staging (False: own launch)
+        # SiLU-mul folded into the down launch's activation staging (two launches instead of three).  OFF: measured slower on
+        # the Mixtral TP-4 shard stack (723 vs 758 tok/s, profiles/r02_moe_decode_notes.md) — every CTA of a rank recomputes the
+        # row's exp() on the critical path between the PDL wait and its first mma, while the separate 2 us kernel overlaps
+        self.fuse_act = False
         self._stack = None
         if grouped is None or grouped:
             self._stack = self._build_stack()
