@@ -510,7 +510,8 @@ def extra_workloads(args, device, rank, world, peaks):
             alg = (att + exp) * c["layers"]
             ms, fin = time_stack(st, 1, world, device, 10, c["hidden"], runner=run_mixtral)
             ms8, _ = time_stack(st, 8, world, device, 5, c["hidden"], runner=run_mixtral)
-            return {"workload": "Mixtral-8x7B int4 g64 asym, TP-4, experts through the grouped MoE kernels "
+            return {"workload": "Mixtral-8x7B int4 g64 asym, TP-4, experts through gptqmodel_b200.moe.MoEExperts (one token: "
+                                "decode-tier MoE launches, 8 tokens: grouped small-batch kernels) "
                                 "(BASELINE configs[4])" + ("" if world == 4 else
                                                            ": ONE rank's shard stack on one GPU, no all-reduce"),
                     "decode_tok_s": 1e3 / ms, "decode_frac_hbm_per_gpu": alg / (ms * 1e-3) / 1e9 / hbm,
